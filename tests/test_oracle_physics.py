@@ -1,0 +1,143 @@
+"""Pins the CPU oracle's rigid-body dynamics to physics itself (the reference ships no golden
+vectors): independent numpy formulations and conservation laws."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from phase_guided_terrain_traversal_b200 import model as gm
+
+
+def rand_state(rng, z=1.0):
+    qpos = np.zeros(19)
+    qpos[0:3] = [rng.uniform(-1, 1), rng.uniform(-1, 1), z]
+    q = rng.normal(size=4)
+    qpos[3:7] = q / np.linalg.norm(q)
+    qpos[7:] = np.array([0, 0.9, -1.8] * 4) + rng.uniform(-0.4, 0.4, 12)
+    qvel = rng.normal(size=18) * np.array([1, 1, 1, 2, 2, 2] + [4] * 12)
+    return qpos, qvel
+
+
+def test_mass_matrix_matches_jacobian_sum(flat_model, train_cfg):
+    rng = np.random.default_rng(0)
+    orc = Oracle(flat_model, train_cfg, 4, "f64")
+    qs = [rand_state(rng) for _ in range(4)]
+    orc.set("qpos", np.stack([q for q, _ in qs]))
+    orc.set("qvel", np.zeros((4, 18)))
+    orc.set("ctrl", np.stack([q[7:] for q, _ in qs]))
+    orc.forward()
+    M = orc.get("qM").reshape(4, 18, 18)
+    for i, (q, _) in enumerate(qs):
+        Mref, kin = gm.mass_matrix(flat_model, q)
+        assert np.allclose(M[i], Mref, rtol=1e-10, atol=1e-12)
+        assert np.allclose(M[i], M[i].T)
+        assert np.linalg.eigvalsh(M[i]).min() > 0
+        assert np.allclose(orc.get("xpos")[i].reshape(14, 3), kin["xpos"], atol=1e-12)
+        assert np.allclose(orc.get("ximat")[i].reshape(14, 3, 3)[1:], kin["ximat"][1:], atol=1e-12)
+
+
+def test_gravity_bias_is_potential_gradient(flat_model, train_cfg):
+    rng = np.random.default_rng(1)
+    orc = Oracle(flat_model, train_cfg, 1, "f64")
+    q, _ = rand_state(rng)
+    orc.set("qpos", q); orc.set("qvel", np.zeros(18)); orc.set("ctrl", q[7:])
+    orc.forward()
+    bias = orc.get("qfrc_bias")[0]
+    eps = 1e-6
+    for j in range(12):
+        qp, qm = q.copy(), q.copy()
+        qp[7 + j] += eps; qm[7 + j] -= eps
+        dV = (gm.potential_energy(flat_model, qp) - gm.potential_energy(flat_model, qm)) / (2 * eps)
+        assert abs(bias[6 + j] - dV) < 1e-6
+    assert abs(bias[2] - flat_model.body_mass.sum() * 9.81) < 1e-9
+    assert np.allclose(bias[0:2], 0, atol=1e-12)
+
+
+def test_free_fall_and_actuator(flat_model, train_cfg):
+    orc = Oracle(flat_model, train_cfg, 1, "f64")
+    q = flat_model.home_qpos.copy(); q[2] = 2.0
+    orc.set("qpos", q); orc.set("qvel", np.zeros(18)); orc.set("ctrl", q[7:])
+    orc.forward()
+    qacc = orc.get("qacc")[0]
+    # PD torque is zero at ctrl == q, so every body falls with g: joint accelerations vanish
+    assert np.allclose(qacc[2], -9.81, atol=1e-9)
+    assert np.allclose(np.delete(qacc, 2), 0, atol=1e-8)
+    # accelerometer reads 0 in free fall, +g at rest is checked in test_standing
+    assert np.allclose(orc.get("sensordata")[0, 3:6], 0, atol=1e-8)
+    # actuator: kp (ctrl - q) - kv qd, clamped at +-24, FR FL RR RL order
+    ctrl = q[7:].copy(); ctrl[1] += 0.1          # actuator 1 = FR_thigh -> dof 10
+    orc.set("ctrl", ctrl); orc.forward()
+    f = orc.get("actuator_force")[0]
+    assert np.isclose(f[1], 40 * 0.1) and np.count_nonzero(f) == 1
+    assert np.isclose(orc.get("qfrc_actuator")[0, 10], 4.0)
+    ctrl[1] = 2.4; orc.set("ctrl", ctrl); orc.forward()
+    assert orc.get("actuator_force")[0, 1] == 24.0
+    ctrl[1] = 5.0; orc.set("ctrl", ctrl); orc.forward()   # ctrlrange upper 2.5 -> 40*(2.5-.9) = 64 -> clamp 24
+    assert orc.get("actuator_force")[0, 1] == 24.0
+
+
+def _energy_momentum(model, q, v):
+    M, kin = gm.mass_matrix(model, q)
+    T = 0.5 * v @ M @ v
+    V = gm.potential_energy(model, q)
+    # linear / angular momentum about the world origin from body twists
+    p = np.zeros(3); L = np.zeros(3)
+    for b in range(1, 14):
+        jp, jr = gm.jacobian(model, kin, kin["xipos"][b], b)
+        vb, wb = jp @ v, jr @ v
+        Iw = kin["ximat"][b] @ np.diag(model.body_inertia[b]) @ kin["ximat"][b].T
+        p += model.body_mass[b] * vb
+        L += np.cross(kin["xipos"][b], model.body_mass[b] * vb) + Iw @ wb
+    com = (model.body_mass[:, None] * kin["xipos"]).sum(0) / model.body_mass.sum()
+    return T + V, p, L - np.cross(com, p)
+
+
+def test_free_flight_conserves_energy_and_momentum(flat_model, train_cfg):
+    """No damping, no actuation, no contact: E, horizontal momentum and spin about the COM are
+    invariants; this exercises kinematics, CRBA, RNE (Coriolis/centrifugal) and the integrator."""
+    import copy
+    m = copy.deepcopy(flat_model)
+    m.dof_damping[:] = 0; m.act_gainprm[:] = 0; m.act_biasprm[:] = 0
+    m.dof_armature[:] = 0                       # armature is not part of the rigid-body energy
+    m.timestep = 2e-4
+    orc = Oracle(m, train_cfg, 1, "f64")
+    rng = np.random.default_rng(2)
+    q, v = rand_state(rng, z=50.0)
+    orc.set("qpos", q); orc.set("qvel", v); orc.set("ctrl", q[7:])
+    E0, p0, L0 = _energy_momentum(m, q, v)
+    v[6:] *= 0.5                                  # stay clear of the joint limits (they dissipate)
+    orc.set("qvel", v)
+    E0, p0, L0 = _energy_momentum(m, q, v)
+    T0 = E0 - gm.potential_energy(m, q)
+    nstep = 250
+    for _ in range(nstep):
+        orc.physics_step()
+        assert np.abs(orc.get("efc_force")).max() == 0.0
+    q1, v1 = orc.get("qpos")[0], orc.get("qvel")[0]
+    E1, p1, L1 = _energy_momentum(m, q1, v1)
+    t = nstep * m.timestep
+    # first-order integrator: errors are O(dt); bounds are ~5x the measured drift at this dt
+    assert abs(E1 - E0) < 2e-3 * T0
+    assert np.allclose(p1[:2], p0[:2], atol=2e-3)
+    assert np.isclose(p1[2], p0[2] - m.body_mass.sum() * 9.81 * t, atol=2e-3)
+    assert np.allclose(L1, L0, atol=2e-3 * np.linalg.norm(L0))
+
+
+def test_standing_on_floor(flat_model, train_cfg):
+    orc = Oracle(flat_model, train_cfg, 1, "f64")
+    q = flat_model.home_qpos.copy()
+    orc.set("qpos", q); orc.set("qvel", np.zeros(18)); orc.set("ctrl", q[7:])
+    for _ in range(400):                          # 2 s
+        orc.physics_step()
+    orc.forward()
+    q1 = orc.get("qpos")[0]
+    assert 0.2 < q1[2] < 0.32 and np.abs(orc.get("qvel")[0]).max() < 0.05
+    f, k = orc.contacts(0)
+    assert (f[:4, 0] < 0).all() and (k[:4, 4] == -1).all()
+    # total normal force = weight: sum of efc_force over pyramid rows (each row ~ normal + mu*tangent)
+    ef = orc.get("efc_force")[0]
+    J = orc.get("efc_J")[0].reshape(44, 18)
+    fz = (J.T @ ef)[2]
+    assert np.isclose(fz, flat_model.body_mass.sum() * 9.81, rtol=2e-2)
+    s = orc.get("sensordata")[0]
+    assert np.allclose(s[3:6], [0, 0, 9.81], atol=0.3)     # accelerometer at rest
+    assert s[24] > 0.99                                     # up-vector
