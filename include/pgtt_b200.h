@@ -1,0 +1,157 @@
+/* pgtt_b200.h - C ABI of the B200-native GO2 PGTT environment (libpgtt_b200.so).
+ *
+ * Drop-in boundary for the reference's batched env hot path.  The reference has no FFI of its own
+ * (it is Python over JAX); the entry points below are what a binding for that path needs, one per
+ * reference call:
+ *
+ *   pgtt_create            Go2Env.__init__ / Joystick.__init__      go2/base.py:45-113, go2/joystick_pgtt.py:38-48
+ *   pgtt_set_terrain_table jnp.load(terrain_file) + partial(domain_randomize, terrain_matrix=...)
+ *                                                                    training/train.py:165-170
+ *   pgtt_randomize         domain_randomize(model, rng, terrain)     go2/randomize.py:23-171, randomize_simple.py:24-138
+ *   pgtt_reset             Joystick.reset (+ wrapper resets)         go2/joystick_pgtt.py:50-131
+ *   pgtt_step              wrapped env.step                          go2/joystick_pgtt.py:141-231, training/train.py:255
+ *   pgtt_heightscan        create_sensor_matrix                      go2/heightmap.py:25-67
+ *   pgtt_forward           mjx.forward on the current state          go2/joystick_pgtt.py:78
+ *   pgtt_policy_step /     brax ppo acting step + generate_unroll    training/train.py:135-161,242-263
+ *   pgtt_rollout
+ *   pgtt_get_buffers       State / info / data field access          go2/joystick_pgtt.py:101-131
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on success or
+ * a negative pgtt_status; pgtt_last_error() gives the message of the last failure on the calling
+ * thread.  A handle is bound to one device and is NOT thread-safe.  All launches are asynchronous on
+ * the caller's stream (a cudaStream_t passed as void*; NULL = default stream); no entry point
+ * synchronises the host except pgtt_create / pgtt_destroy / pgtt_set_terrain_table / pgtt_sync.
+ * Per-env arrays are row-major [num_envs][dim] in DEVICE memory owned by the handle.
+ */
+#ifndef PGTT_B200_H
+#define PGTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGTT_NQ 19
+#define PGTT_NV 18
+#define PGTT_NU 12
+#define PGTT_NBOX 100
+#define PGTT_NRAY 117          /* 13 x 9 */
+#define PGTT_NOBS 171
+#define PGTT_NPRIV 215
+#define PGTT_NMETRIC 22        /* 21 reward terms (order of go2/configs.py:31-59) + swing_peak */
+#define PGTT_NSENSOR 49
+#define PGTT_NCON 8            /* 4 foot-plane + <=4 foot-box contacts (max_contact_points) */
+#define PGTT_NEPMETRIC 24      /* sum_reward, length, 22 metrics */
+
+typedef enum {
+  PGTT_OK = 0,
+  PGTT_ERR_ARG = -1,           /* bad argument / model outside the supported family */
+  PGTT_ERR_CUDA = -2,          /* CUDA runtime error (message has the cudaError string) */
+  PGTT_ERR_STATE = -3,         /* call order (e.g. stairs task stepped before a terrain table was set) */
+  PGTT_ERR_NOMEM = -4
+} pgtt_status;
+
+/* Compiled model constants (float64 on the host side; see model.py:Go2Model). Bodies 1..13 =
+ * base, FL_{hip,thigh,calf}, FR_*, RL_*, RR_*; hinges 0..11 in that (qpos) order; actuators in MJCF
+ * order FR, FL, RR, RL. */
+typedef struct {
+  double timestep, gravity[3], impratio, tolerance, ls_tolerance, meaninertia;
+  int iterations, ls_iterations, max_geom_pairs, max_contact_points, n_boxes;
+  double body_pos[14][3], body_ipos[14][3], body_iquat[14][4], body_mass[14], body_inertia[14][3];
+  double body_invweight0[14][2];
+  double jnt_range[12][2], jnt_solref[2], jnt_solimp[5];
+  double qpos0[19], dof_armature[18], dof_damping[18], dof_invweight0[18];
+  int act_dof[12];
+  double act_gain[12], act_bias[12][3], act_ctrlrange[12][2], act_forcerange[12][2];
+  int foot_geom_id[4];         /* FL FR RL RR */
+  double foot_pos[3], foot_radius, foot_friction[3], foot_solref[2], foot_solimp[5], foot_margin;
+  int floor_geom_id, box_geom_id0;
+  double floor_friction[3], floor_solref[2], floor_solimp[5];
+  double box_rbound, box_friction[3], box_solref[2], box_solimp[5];
+  double imu_pos[3];
+  int n_model_bodies;          /* nbody of the MJCF scene (14 or 114): length of the body-mass DR draw */
+} pgtt_model_desc;
+
+/* Task configuration = go2/configs.py:default_config() flattened. */
+typedef struct {
+  double ctrl_dt, action_scale, noise_level;
+  double noise_joint_pos, noise_joint_vel, noise_gyro, noise_gravity, noise_linvel, noise_heightscan;
+  double reward_scale[21];     /* order of go2/configs.py:31-59 */
+  double tracking_sigma, swing_height, base_feet_distance, phase_sigma;
+  double cmd_u_max[3], cmd_u_min[3], cmd_b[3], gait_freq[2];
+  double soft_limit_factor;
+  double default_pose[12], home_qpos[19];
+  int history_update_steps, episode_length, n_substeps;
+  int rng_partitionable;       /* jax_threefry_partitionable: 1 = JAX >= 0.5 default */
+} pgtt_task_desc;
+
+/* Device pointers into the handle's state, [num_envs][dim] row-major. float unless noted. */
+typedef struct {
+  int num_envs;
+  /* mjx.Data fields the task reads or exposes */
+  float *qpos, *qvel, *qacc, *qacc_warmstart, *ctrl, *time;
+  float *sensordata, *actuator_force, *site_xpos /*[5][3] imu FL FR RL RR*/, *site_xmat /*[9] imu*/;
+  float *contact_dist /*[8]*/;
+  int32_t *contact_geom /*[8][2]*/;
+  int32_t *solver_niter /*[n_substeps]*/;
+  /* State */
+  float *obs_state, *obs_privileged, *reward, *done, *metrics;
+  /* info (go2/joystick_pgtt.py:101-120) */
+  uint32_t *rng /*[2]*/;
+  float *command;
+  int32_t *step, *steps_until_next_cmd;
+  float *phase, *phase_dt, *gait_freq, *last_act, *last_last_act, *feet_air_time;
+  int32_t *last_contact /*[4]*/;
+  float *swing_peak, *H_max, *H_min, *heightscan /*[117][3]*/, *motor_targets;
+  float *qpos_error_history /*[24]*/, *qvel_history /*[24]*/;
+  int32_t *contact /*[4] FR FL RR RL, this step*/, *first_contact /*[4]*/;
+  /* wrapper keys (brax EpisodeWrapper / playground BraxAutoResetWrapper) */
+  float *steps, *truncation, *episode_done, *episode_metrics /*[24]*/;
+  float *first_qpos, *first_qvel, *first_qacc_warmstart, *first_obs_state, *first_obs_privileged;
+  /* per-env model written by pgtt_randomize (go2/randomize.py:140-169) */
+  float *body_mass /*[13] bodies 1..13*/, *body_ipos_base /*[3]*/, *dof_armature /*[12]*/, *dof_damping /*[12]*/;
+  float *actuator_gain /*[12]*/, *actuator_bias1 /*[12]*/, *qpos0 /*[12]*/, *box_friction /*[100]*/, *floor_friction /*[1]*/;
+  int32_t *terrain_index;
+} pgtt_buffers;
+
+typedef struct pgtt_env pgtt_env;
+
+const char* pgtt_last_error(void);
+int pgtt_version(void);
+
+int pgtt_create(const pgtt_model_desc* model, const pgtt_task_desc* task, int device, int num_envs, pgtt_env** out);
+int pgtt_destroy(pgtt_env* env);
+int pgtt_sync(pgtt_env* env, void* stream);
+
+/* boxes: HOST float32 [n_terrains][100][10] = pos xyz | quat wxyz | half-size xyz (terrains/level*.npy).
+ * Only yaw-rotated boxes (quat x = y = 0) are supported - true for every file the generator writes. */
+int pgtt_set_terrain_table(pgtt_env* env, const float* boxes, int n_terrains);
+
+/* keys: DEVICE uint32 [num_envs][2] (jax PRNG keys). dynamics = 0 assigns terrain only. */
+int pgtt_randomize(pgtt_env* env, const uint32_t* keys, int dynamics, void* stream);
+int pgtt_reset(pgtt_env* env, const uint32_t* keys, void* stream);
+
+/* action: DEVICE float [num_envs][12]. wrapped != 0 applies EpisodeWrapper + auto-reset semantics. */
+int pgtt_step(pgtt_env* env, const float* action, int wrapped, void* stream);
+
+/* mjx.forward on the current qpos/qvel/ctrl (refreshes sensordata, contacts, qacc, warmstart). */
+int pgtt_forward(pgtt_env* env, void* stream);
+
+/* create_sensor_matrix: center DEVICE [num_envs][3], yaw DEVICE [num_envs] -> out DEVICE [num_envs][117][3]. */
+int pgtt_heightscan(pgtt_env* env, const float* center, const float* yaw, float* out, void* stream);
+
+int pgtt_get_buffers(pgtt_env* env, pgtt_buffers* out);
+
+/* Debug / parity probe: one mjx.forward with every intermediate written to `out`
+ * (DEVICE float [num_envs][PGTT_DEBUG_FLOATS]); layout in csrc/pgtt_debug.h. */
+#define PGTT_DEBUG_FLOATS 2048
+int pgtt_debug_forward(pgtt_env* env, float* out, void* stream);
+
+/* Counters the bench reports: kernels launched by this handle since creation. */
+int64_t pgtt_launch_count(pgtt_env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

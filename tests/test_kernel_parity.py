@@ -1,0 +1,215 @@
+"""Kernel vs CPU oracle on identical seeded inputs, through the C ABI.
+
+Runs twice: on the host-emulated kernel source (`emu`, CPU) and on the real sm_100a library
+(`cuda`, marked gpu). Tolerances (fp32 kernel vs fp32 oracle, different operation order):
+  * integer / boolean bookkeeping (rng keys, step counters, contact pairs and flags, terrain index,
+    terrain index): EXACT; Newton iteration counts agree up to borderline stops;
+  * kinematics, inertia, bias forces, constraint rows from one `forward`: 1e-5 of the field's max-norm;
+  * solver output qacc (and the accelerometer that reads it): 2e-3 of max|qacc| (solver-limited,
+    SURVEY 8c);
+  * observations / reward / sensors after reset and after each control step: 1e-4 of the field's
+    max-norm (the north-star tolerance), joint velocities and accelerations 2e-3.
+"""
+import numpy as np
+import pytest
+
+from backends import BACKENDS, make_env
+from oracle.oracle import Oracle
+from phase_guided_terrain_traversal_b200 import model as gm
+from phase_guided_terrain_traversal_b200 import terrain as terr_mod
+
+N = 16
+ACT_PERM = [3, 4, 5, 0, 1, 2, 9, 10, 11, 6, 7, 8]
+
+
+def keys_for(n, hi):
+    return np.stack([np.full(n, hi, dtype=np.uint32), np.arange(n, dtype=np.uint32)], 1)
+
+
+def relerr(x, y):
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    return np.abs(x - y).max() / max(np.abs(x).max(), 1e-6)
+
+
+def random_states(m, n, seed):
+    rng = np.random.default_rng(seed)
+    qpos = np.tile(m.home_qpos, (n, 1)); qvel = np.zeros((n, 18))
+    for i in range(n):
+        qpos[i, 0:2] = rng.uniform(-1.5, 1.5, 2); qpos[i, 2] = 0.27 + rng.uniform(-0.01, 0.12)
+        q = np.array([1.0, 0, 0, 0]) + rng.normal(size=4) * 0.15
+        qpos[i, 3:7] = q / np.linalg.norm(q)
+        qpos[i, 7:] += rng.uniform(-0.3, 0.3, 12)
+        qvel[i] = rng.normal(size=18) * np.array([.5] * 3 + [1] * 3 + [3] * 12)
+    ctrl = qpos[:, 7:][:, ACT_PERM] + rng.uniform(-0.3, 0.3, (n, 12))
+    warm = rng.normal(size=(n, 18)) * 10
+    return qpos, qvel, ctrl, warm
+
+
+def setup_pair(kind, task, cfg, dyn=True, part=True, seed_hi=7, level="level07"):
+    m = gm.compile_model(task)
+    orc = Oracle(m, cfg, N, "f32", rng_partitionable=part)
+    env = make_env(kind, m, cfg, N, rng_partitionable=part)
+    keys = keys_for(N, seed_hi)
+    if task == "stairs":
+        table = terr_mod.load_terrain(level)
+        orc.randomize(keys, table, dyn); env.set_terrain(table); env.randomize(keys, dyn)
+    else:
+        orc.randomize(keys, None, dyn); env.randomize(keys, dyn)
+    return m, orc, env, keys
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+@pytest.mark.parametrize("task", ["flat_terrain", "stairs"])
+def test_forward_stage_by_stage(kind, task, train_cfg):
+    m, orc, env, _ = setup_pair(kind, task, train_cfg)
+    # per-env model written by the randomiser is bit-identical
+    assert np.array_equal(orc.get("terrain_index")[:, 0], env.get("terrain_index")[:, 0]) or task == "flat_terrain"
+    for a, b, sl in [("m_body_mass", "body_mass", slice(1, None)), ("m_dof_armature", "dof_armature", slice(6, None)),
+                     ("m_dof_damping", "dof_damping", slice(6, None)), ("m_qpos0", "qpos0", slice(7, None)), ("m_act_gain", "actuator_gain", slice(None))]:
+        assert np.array_equal(orc.get(a)[:, sl].astype(np.float32), env.get(b)), a
+    qpos, qvel, ctrl, warm = random_states(m, N, 3)
+    for k, v in (("qpos", qpos), ("qvel", qvel), ("ctrl", ctrl), ("qacc_warmstart", warm)):
+        orc.set(k, v); env.set(k, v.astype(np.float32))
+    orc.forward()
+    D = env.debug_forward()
+    sl = lambda a, n: D[:, a:a + n]
+    assert relerr(orc.get("xpos").reshape(N, 14, 3)[:, 1:].reshape(N, -1), sl(0, 39)) < 1e-5
+    assert relerr(orc.get("xmat").reshape(N, 14, 9)[:, 1:].reshape(N, -1), sl(39, 117)) < 1e-5
+    assert relerr(orc.get("subtree_com"), sl(195, 3)) < 1e-5
+    assert relerr(orc.get("cinert").reshape(N, 14, 10)[:, 1:].reshape(N, -1), sl(198, 130)) < 1e-5
+    assert relerr(orc.get("cdof"), sl(328, 108)) < 1e-5
+    assert relerr(orc.get("qM"), sl(436, 324)) < 1e-5
+    assert relerr(orc.get("qfrc_bias"), sl(760, 18)) < 1e-5
+    assert relerr(orc.get("qfrc_smooth"), sl(778, 18)) < 1e-5
+    assert relerr(orc.get("qacc_smooth"), sl(796, 18)) < 1e-4
+    assert relerr(orc.get("actuator_force"), sl(1890, 12)) < 1e-5
+    nbox_contacts = 0
+    for i in range(N):  # contact-pair bookkeeping: exact
+        f, k = orc.contacts(i)
+        c = D[i, 832:960].reshape(8, 16)
+        act_o = sorted((int(k[j, 3]), int(k[j, 4])) for j in range(8) if f[j, 0] < 0 and k[j, 3] >= 0)
+        act_k = sorted((int(c[j, 14]), int(c[j, 15])) for j in range(8) if c[j, 0] < 0 and c[j, 15] > -2)
+        assert act_o == act_k, (i, act_o, act_k)
+        nbox_contacts += sum(1 for _, b in act_o if b >= 0)
+        do = {(int(k[j, 3]), int(k[j, 4])): f[j, 0] for j in range(8) if f[j, 0] < 0 and k[j, 3] >= 0}
+        dk = {(int(c[j, 14]), int(c[j, 15])): c[j, 0] for j in range(8) if c[j, 0] < 0 and c[j, 15] > -2}
+        for key in do:
+            assert abs(do[key] - dk[key]) < 1e-6
+    if task == "stairs":
+        assert nbox_contacts > 0
+    # constraint rows: same order in both (12 limits, 4 floor contacts, box contacts by depth)
+    assert relerr(orc.get("efc_J"), sl(1048, 792)) < 1e-5
+    assert relerr(orc.get("efc_D"), sl(960, 44)) < 1e-4
+    assert relerr(orc.get("efc_aref"), sl(1004, 44)) < 1e-4
+    qo, qk = orc.get("qacc"), sl(814, 18)
+    for i in range(N):
+        assert np.abs(qo[i] - qk[i]).max() < 2e-3 * np.abs(qo[i]).max(), i
+    # the Newton loop stops on fp32 cost differences ~1e-8: counts agree except for borderline envs
+    assert (orc.get("solver_niter")[:, 0] != D[:, 1889]).sum() <= 2
+    so, sk = orc.get("sensordata"), sl(1840, 49)
+    acc = np.zeros(49, bool); acc[3:6] = True
+    assert relerr(so[:, ~acc], sk[:, ~acc]) < 1e-5
+    assert relerr(so[:, acc], sk[:, acc]) < 2e-3
+
+
+FLOAT_FIELDS = {  # oracle name -> (abi name, tolerance as a fraction of the field's max-norm)
+    "qpos": ("qpos", 1e-5), "qvel": ("qvel", 2e-3), "obs_state": ("obs_state", 1e-4), "obs_priv": ("obs_privileged", 1e-4),
+    "reward": ("reward", 1e-4), "done": ("done", 0.0), "metrics": ("metrics", 2e-4), "command": ("command", 1e-6), "phase": ("phase", 1e-6),
+    "gait_freq": ("gait_freq", 1e-6), "feet_air_time": ("feet_air_time", 1e-6), "H_max": ("H_max", 1e-5), "H_min": ("H_min", 1e-5),
+    "heightscan": ("heightscan", 1e-5), "sensordata": ("sensordata", 2e-3), "actuator_force": ("actuator_force", 1e-4),
+    "last_act": ("last_act", 0.0), "last_last_act": ("last_last_act", 0.0), "motor_targets": ("motor_targets", 1e-6), "swing_peak": ("swing_peak", 1e-5),
+    "qpos_error_history": ("qpos_error_history", 1e-4), "qvel_history": ("qvel_history", 2e-3), "episode_metrics": ("episode_metrics", 2e-4),
+    "steps": ("steps", 0.0), "truncation": ("truncation", 0.0), "episode_done": ("episode_done", 0.0),
+}
+EXACT_FIELDS = {"rng": "rng", "step": "step", "steps_until_next_cmd": "steps_until_next_cmd", "last_contact": "last_contact",
+                "contact_flags": "contact", "first_contact": "first_contact"}
+
+
+def compare_state(orc, env, tag):
+    for a, b in EXACT_FIELDS.items():
+        assert np.array_equal(orc.get(a), env.get(b).astype(np.float64)), (tag, a)
+    for a, (b, tol) in FLOAT_FIELDS.items():
+        x, y = orc.get(a), env.get(b).astype(np.float64)
+        if a == "obs_priv":   # the accelerometer slice reads the solver output: solver-limited tolerance
+            acc = slice(174, 177)
+            assert np.abs(x[:, acc] - y[:, acc]).max() <= 2e-3 * max(np.abs(x[:, acc]).max(), 1.0), (tag, "accelerometer")
+            x = x.copy(); y = y.copy(); x[:, acc] = 0; y[:, acc] = 0
+        err = np.abs(x - y).max()
+        assert err <= tol * max(np.abs(x).max(), 1.0) + 1e-12, (tag, a, err, np.abs(x).max())
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+@pytest.mark.parametrize("task,part,dyn", [("flat_terrain", True, True), ("stairs", True, True), ("stairs", False, False)])
+def test_reset_and_step_parity(kind, task, part, dyn, train_cfg):
+    """Config-1/2/3 style runs: reset, then control steps with random actions; every State / info
+    field is compared after each call (trajectories stay within tolerance for the first steps)."""
+    m, orc, env, keys = setup_pair(kind, task, train_cfg, dyn=dyn, part=part)
+    orc.reset(keys + 3); env.reset(keys + 3)
+    compare_state(orc, env, "reset")
+    rng = np.random.default_rng(5)
+    for s in range(3):
+        act = rng.uniform(-1, 1, (N, 12)).astype(np.float32)
+        orc.step(act.astype(np.float64)); env.step(act)
+        compare_state(orc, env, f"step{s}")
+    assert (orc.get("solver_niter")[:, 0] != env.get("solver_niter")[:, 3]).sum() <= 2
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_heightscan_matches_oracle_and_numpy(kind, train_cfg):
+    """Ray grid against (a) the oracle's generic slab ray-caster and (b) an independent numpy
+    statement of go2/heightmap.py:25-67 / deploy/cpu_heightmap/heightmap.py:54-109."""
+    m, orc, env, _ = setup_pair(kind, "stairs", train_cfg, dyn=False, level="level13")
+    rng = np.random.default_rng(2)
+    center = np.concatenate([rng.uniform(-3.5, 3.5, (N, 2)), rng.uniform(0.2, 0.8, (N, 1))], 1)
+    yaw = rng.uniform(-np.pi, np.pi, N)
+    ho = orc.scan(center, yaw)
+    hk = np.asarray(env.heightscan(center.astype(np.float32), yaw.astype(np.float32)).cpu() if kind == "cuda" else env.heightscan(center.astype(np.float32), yaw.astype(np.float32)))
+    assert np.abs(ho[..., :2] - hk[..., :2]).max() < 1e-5
+    dz = np.abs(ho[..., 2] - hk[..., 2])
+    assert (dz < 1e-5).mean() > 0.995     # a ray within 1 ulp of a box edge may land on either side
+    assert ho[..., 2].max() > 0.05        # the scans do see boxes
+    # numpy restatement for env 0
+    table = terr_mod.load_terrain("level13")
+    boxes = table[int(orc.get("terrain_index")[0, 0])]
+    c, s = np.cos(yaw[0]), np.sin(yaw[0])
+    p, k = np.meshgrid((6 - np.arange(13)) * 0.1, (4 - np.arange(9)) * 0.1, indexing="ij")
+    off = np.stack([p, k], -1) @ np.array([[c, s], [-s, c]])
+    xy = center[0, :2] + off
+    xy[6, 4] = center[0, :2]
+    z = np.zeros((13, 9))
+    for b in boxes:
+        cw, sw = b[3] ** 2 - b[6] ** 2, 2 * b[3] * b[6]
+        rel = xy - b[:2]
+        lx, ly = cw * rel[..., 0] + sw * rel[..., 1], -sw * rel[..., 0] + cw * rel[..., 1]
+        inside = (np.abs(lx) <= b[7]) & (np.abs(ly) <= b[8])
+        z = np.where(inside, np.maximum(z, b[2] + b[9]), z)
+    assert (np.abs(z - hk[0, ..., 2]) < 1e-5).mean() > 0.98
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_autoreset_and_episode_wrapper(kind, train_cfg):
+    """Fallen robots (up-vector z < 0) end the episode; the wrapper restores the cached first
+    data/obs but keeps info. Checked against the oracle's wrapper."""
+    import copy
+    cfg = copy.deepcopy(train_cfg)
+    cfg.episode_length = 3
+    m, orc, env, keys = setup_pair(kind, "flat_terrain", cfg, dyn=False)
+    orc.reset(keys); env.reset(keys)
+    first_q = env.get("qpos").copy(); first_obs = env.get("obs_state").copy()
+    # flip half of the robots upside down
+    q = orc.get("qpos"); q[::2, 3:7] = [0, 1, 0, 0]; q[::2, 2] = 0.4
+    orc.set("qpos", q); env.set("qpos", q.astype(np.float32))
+    rng = np.random.default_rng(0)
+    for s in range(4):
+        act = rng.uniform(-1, 1, (N, 12)).astype(np.float32)
+        orc.step(act.astype(np.float64)); env.step(act)
+        d = env.get("done")[:, 0]
+        assert np.array_equal(d, orc.get("done")[:, 0])
+        if s == 0:
+            assert d[::2].all() and not d[1::2].any()
+            assert np.array_equal(env.get("qpos")[::2], first_q[::2]) and np.array_equal(env.get("obs_state")[::2], first_obs[::2])
+            assert (env.get("step")[:, 0] == 1).all()          # info is not reset
+        if s == 2:
+            assert d[1::2].all()                               # truncation at episode_length = 3
+            assert np.array_equal(env.get("truncation")[1::2, 0], np.ones(N // 2))
+        compare_state(orc, env, f"wrapped step{s}")
