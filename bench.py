@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/sec of the batched GO2 PGTT step (BASELINE.json metric) on N B200s.
+
+Workload (N=1): BASELINE config[1] = `Joystick("stairs")` on terrains/level1.npy, 4096 envs, no
+dynamics DR (terrain assignment only), synthetic random joystick commands (env-internal
+`sample_command`) and U(-1,1) actions, episode wrapper + auto-reset on. One "step" = one wrapped
+`env.step` over all envs = 4 physics substeps + contacts + ray grid + obs + reward, ONE kernel launch.
+N>1: every rank owns its own 4096 envs (index sharding, no collective in the data path) -> weak scaling.
+
+Timed regions (device time, CUDA events on the launching stream, max over ranks):
+  value            K steps, each bracketed by its own event pair, L2 flushed (256 MiB write) between
+                   steps - the state of 4096 envs (~20 MB) would otherwise stay L2-resident;
+  value_l2_resident the same K steps back to back with no flush (how a rollout actually runs);
+  e2e              K steps through the public API with HOST (pinned) actions: H2D copy of the
+                   actions, step, D2H of reward+done, host sync every step.
+`--impl reference` times the CPU restatement of the reference step (oracle/, fp32, OpenMP over envs,
+all host threads) - the reference's own MJX stack is not installable here or on the GPU box
+(no jax / mujoco wheels, no network), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import functools
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np
+
+METRIC = "env-steps/sec (batched GO2 PGTT step)"
+UNIT = "env-steps/s"
+# algorithmic bytes per env-step of the fused step kernel (SURVEY.md 8d / DESIGN.md): 852 B read + 2700 B written
+B_ALG = 3552
+FLOP_PER_ENV_STEP = 0.75e6     # SURVEY.md 8d estimate, used only for the secondary fp32 figure
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--num-envs", type=int, default=4096, help="envs per GPU")
+    p.add_argument("--task", default="stairs")
+    p.add_argument("--terrain", default="level1")
+    p.add_argument("--dr", type=int, default=0, help="1 = full go2/randomize.py dynamics DR (config 3)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
+    return p.parse_args()
+
+
+def load_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed regions
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle): the ONLY place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------------
+def make_oracle(args, n, cfg, table, seed_offset=0):
+    from oracle.oracle import Oracle
+    from phase_guided_terrain_traversal_b200 import model as gm, prng
+    m = gm.compile_model(args.task, sim_dt=cfg.sim_dt, Kp=cfg.Kp, Kd=cfg.Kd)
+    orc = Oracle(m, cfg, n, "f32native")   # gcc -O3 -march=native, built on this host
+    keys = prng.env_keys(0, n, seed_offset)
+    orc.randomize(keys, table if args.task == "stairs" else None, bool(args.dr))
+    orc.reset(keys + np.uint32(1))
+    return orc
+
+
+def time_oracle(orc, n, steps, warmup, seed=99):
+    g = np.random.default_rng(seed)
+    acts = [g.uniform(-1, 1, (n, 12)) for _ in range(8)]
+    for i in range(warmup):
+        orc.step(acts[i % 8], wrapped=True)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        orc.step(acts[i % 8], wrapped=True)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args, cfg, table, budget_s):
+    cores = os.cpu_count() or 1
+    n = 16 * cores
+    orc = make_oracle(args, n, cfg, table)
+    t1 = time_oracle(orc, n, 2, 3)
+    per_step = t1 / 2
+    steps = int(max(5, min(2000, budget_s / max(per_step, 1e-6))))
+    t = time_oracle(orc, n, steps, 0)
+    return {"value": n * steps / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} envs x {steps} wrapped steps of the same workload ({args.task}/{args.terrain}, dr={args.dr}), fp32 C oracle (gcc -O3 -march=native), OpenMP over envs, {t:.1f} s"}
+
+
+def run_reference(args, cfg, table, rank):
+    """--impl reference: the CPU restatement on all host threads; each step = a bounded sample of envs."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    probe_n = 16 * cores
+    orc = make_oracle(args, probe_n, cfg, table)
+    per_env_step = time_oracle(orc, probe_n, 2, 3) / (2 * probe_n)
+    total_steps = args.steps + args.warmup
+    n = int(max(cores, min(args.num_envs, 60.0 / max(per_env_step * total_steps, 1e-9))))
+    n = max(cores, (n // cores) * cores)
+    del orc
+    orc = make_oracle(args, n, cfg, table)
+    t = time_oracle(orc, n, args.steps, max(args.warmup, 3))
+    v = n * args.steps / t
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": workload_config(args, n, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"each step = {n} envs (bounded sample of the {args.num_envs}-env workload), fp32 C restatement of the MJX step, OpenMP over envs"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference MJX/JAX stack not installable (no jax/mujoco wheels, no network): this is the restated CPU oracle, not MJX",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_per_gpu, n_gpus):
+    return {"workload": f"GO2 joystick_pgtt {args.task} terrains/{args.terrain}.npy, {n_per_gpu} envs/GPU x {n_gpus} GPU, "
+                        f"{'randomize.py on' if args.dr else 'no DR (terrain assignment only)'}, wrapped step (episode + auto-reset), 4 substeps",
+            "num_envs_per_gpu": n_per_gpu, "task": args.task, "terrain": args.terrain, "dr": bool(args.dr),
+            "actions": "U(-1,1), pool of 16 pre-generated device buffers", "l2": "flushed between timed steps (256 MiB write); value_l2_resident = back-to-back"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    from phase_guided_terrain_traversal_b200 import prng, terrain
+    from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
+    cfg = training_overrides(default_config())
+    table = terrain.load_terrain(args.terrain) if args.task == "stairs" else None
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, table, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    from phase_guided_terrain_traversal_b200.go2 import randomize, randomize_simple
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+
+    N = args.num_envs
+    keys = prng.env_keys(0, N, offset=rank * N)
+    env = Joystick(task=args.task, config=cfg, device=local_rank)
+    if args.task == "stairs":
+        rfn = functools.partial(randomize.domain_randomize, rng=keys, terrain_matrix=table, dynamics=bool(args.dr))
+    else:
+        rfn = functools.partial(randomize_simple.domain_randomize, rng=keys, dynamics=bool(args.dr))
+    wenv = wrap_for_brax_training(env, episode_length=cfg.episode_length, action_repeat=1, randomization_fn=rfn)
+    state = wenv.reset(keys + np.uint32(1))
+    abi = env._abi
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    pool = [torch.rand((N, 12), generator=g, device=dev) * 2 - 1 for _ in range(16)]
+    host_pool = [a.cpu().pin_memory() for a in pool]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        wenv.step(state, pool[i % 16])
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- region A: back-to-back (L2-resident state) ------------------------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        abi.step_ptr(pool[i % 16].data_ptr(), wrapped=True)
+    e1.record(stream)
+    barrier()
+    ms_resident = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- region B: one event pair per step, L2 flushed between steps (the reported `value`) ----------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    l0 = abi.launch_count()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        a, b = evs[i]
+        a.record(stream)
+        abi.step_ptr(pool[i % 16].data_ptr(), wrapped=True)
+        b.record(stream)
+    barrier()
+    launches = abi.launch_count() - l0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ms_cold = max_over_ranks(float(sum(step_ms)))
+    kernel_ms = float(np.mean(step_ms))     # one event pair brackets exactly one pgtt_env_kernel<STEP> launch
+
+    # ---- region C: end to end through the public API with host actions ---------------------------------
+    rew_host = torch.empty((2, N), dtype=torch.float32).pin_memory()
+    for i in range(3):
+        st = wenv.step(state, host_pool[i % 16])
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        st = wenv.step(state, host_pool[i % 16])                 # H2D (pinned, async) + fused step kernel
+        rew_host[0].copy_(st.reward, non_blocking=True)          # D2H of the step's result
+        rew_host[1].copy_(st.done, non_blocking=True)
+        stream.synchronize()                                     # the host consumes reward/done every step
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    sampler.stop()
+
+    done_rate = float(state.done.float().mean().item())
+    niter = float(abi.buf["solver_niter"].float().mean().item())
+    finite = bool(torch.isfinite(state.data.qpos).all().item())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        total_envs = N * world
+        value = total_envs * K / (ms_cold * 1e-3)
+        achieved = B_ALG * N / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_cold / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, N, world),
+            "value_l2_resident": total_envs * K / (ms_resident * 1e-3), "ms_per_step_l2_resident": ms_resident / K,
+            "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * 12 * 4, "d2h_bytes_per_step": N * 2 * 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "pgtt_env_kernel<OP_STEP>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_env_step": B_ALG,
+                         "note": "kernel is fp32-issue/latency bound, not HBM bound (SURVEY 8d, DESIGN.md): ~210 FLOP/B",
+                         "fp32_tflops_est": FLOP_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e12},
+            "clocks": sampler.summary(),
+            "health": {"done_rate_last_step": done_rate, "solver_niter_mean": niter, "state_finite": finite},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cfg, table, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,10 +29,24 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", str(HERE), "-B" if force else "-s", "all"], check=True, capture_output=True)
 
 
+def build_native() -> Path:
+    """fp32 oracle compiled for THIS host (-O3 -march=native): the CPU-baseline build of bench.py.
+    Always rebuilt (a library built on another machine may use instructions this CPU lacks)."""
+    import os
+    import tempfile
+    out = Path(tempfile.gettempdir()) / f"liborc_f32_native_{os.getpid()}.so"
+    subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-fopenmp", "-std=gnu11", "-DORC_F32", "-o", str(out),
+                    str(HERE / "pgtt_oracle.c"), "-lm"], check=True, capture_output=True)
+    return out
+
+
 def _lib(precision: str):
     if precision not in _LIBS:
-        build()
-        lib = ctypes.CDLL(str(HERE / "_build" / f"liborc_{precision}.so"))
+        if precision == "f32native":
+            lib = ctypes.CDLL(str(build_native()))
+        else:
+            build()
+            lib = ctypes.CDLL(str(HERE / "_build" / f"liborc_{precision}.so"))
         lib.orc_create.restype = ctypes.c_void_p
         lib.orc_create.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         lib.orc_destroy.argtypes = [ctypes.c_void_p]

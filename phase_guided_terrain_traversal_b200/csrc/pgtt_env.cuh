@@ -57,7 +57,7 @@ DEV uint32_t rng_bits(Key k, int n, int i) {
   return which ? t.b : t.a;
 }
 DEV float rng_unit(Key k, int n, int i) { return __uint_as_float((rng_bits(k, n, i) >> 9) | 0x3F800000u) - 1.0f; }
-DEV float rng_uniform(Key k, int n, int i, float lo, float hi) { return fmaxf(lo, rng_unit(k, n, i) * (hi - lo) + lo); }
+DEV float rng_uniform(Key k, int n, int i, float lo, float hi) { return fmaxf(lo, mul_add_nofma(rng_unit(k, n, i), hi - lo, lo)); }
 DEV int rng_randint(Key k, int lo, int hi) {  // shape (1,)
   const Key k1 = rng_split(k, 2, 0), k2 = rng_split(k, 2, 1);
   const uint32_t hb = rng_bits(k1, 1, 0), lb = rng_bits(k2, 1, 0);

@@ -26,6 +26,8 @@ DEV float ldg(const float* p) { return __ldg(p); }
 DEV int popc(unsigned x) { return __popc(x); }
 DEV float rsqrt_(float x) { return rsqrtf(x); }
 DEV void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+// un-contracted multiply-add: random draws must not depend on whether the compiler forms an FMA
+DEV float mul_add_nofma(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
 #endif
 
 DEV float warp_sum(float v) {

@@ -79,6 +79,7 @@ DEV float ldg(const float* p) { return *p; }
 DEV int popc(unsigned x) { return __builtin_popcount(x); }
 DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
 DEV void sincos_(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
+DEV float mul_add_nofma(float a, float b, float c) { return a * b + c; }  // built with -ffp-contract=off
 DEV float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 DEV int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 DEV float __uint_as_float(uint32_t i) { float f; memcpy(&f, &i, 4); return f; }
