@@ -18,10 +18,34 @@
 #include "pgtt_debug.h"
 #include "pgtt_env.cuh"
 
-#define WARPS_PER_BLOCK 4
+#define MAX_WARPS_PER_BLOCK 16
 #define WS_BYTES ((sizeof(WS) + 15) / 16 * 16)
 
 static thread_local std::string g_err;
+
+// Warps (= envs) per CTA, one CTA per SM: the warps of a CTA run the stages in lockstep so the
+// instruction stream is fetched once per CTA. Picks the count in [8, 16] that wastes the fewest
+// warp slots in the last wave over the SMs (4096 envs on 148 SMs -> 14 warps, 293 CTAs = 1.98 waves).
+// PGTT_WARPS_PER_BLOCK overrides (tuning / tests).
+static int pick_warps_per_block(int n_envs) {
+  if (const char* s = getenv("PGTT_WARPS_PER_BLOCK")) {
+    const int v = atoi(s);
+    if (v >= 1 && v <= MAX_WARPS_PER_BLOCK) return v;
+  }
+  int n_sm = 148;
+#ifndef PGTT_HOST_EMU
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+#endif
+  int best = MAX_WARPS_PER_BLOCK;
+  double best_cost = 1e30;
+  for (int w = MAX_WARPS_PER_BLOCK; w >= 8; w--) {
+    const long ctas = (n_envs + w - 1) / w, waves = (ctas + n_sm - 1) / n_sm;
+    const double cost = (double)waves * (1.0 + 0.02 * w);   // time ~ waves x (mildly growing per-wave time)
+    if (cost < best_cost - 1e-12) { best_cost = cost; best = w; }
+  }
+  return best;
+}
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 // ----------------------------------------------------------------------------------------------
@@ -34,9 +58,9 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
   if (lane < NU) w.ctrl[lane] = B.ctrl[env * NU + lane];
   syncwarp();
   kinematics(w, lane);
+  collision(w, B, env, lane);
   com_inertia_cdof(w, lane);
   crb_and_inertia(w, lane);
-  collision(w, B, env, lane);
   velocity_rne(w, lane);
   smooth_forces(w, lane);
   Rows R;
@@ -113,12 +137,18 @@ DEV void dispatch(WS& w, const LaunchArgs& a, int env, int lane) {
   } while (0)
 
 template <int OP>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) pgtt_env_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 1) pgtt_env_kernel(LaunchArgs a) {
   extern __shared__ float4 smem4[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (env >= a.B.N) return;
+  const int wpb = blockDim.x >> 5;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * wpb + warp;
+  if (env >= a.B.N) return;   // warp-uniform (warp_index is a broadcast): no collective sees a partial warp
   WS& w = *reinterpret_cast<WS*>(reinterpret_cast<char*>(smem4) + (size_t)warp * WS_BYTES);
+  {
+    const int live = a.B.N - blockIdx.x * wpb;
+    if (lane == 0) w.bar_threads = 32 * (live < wpb ? live : wpb);
+    syncwarp();
+  }
   if (OP == OP_STEP) env_step(w, a.B, a.action, env, lane, a.wrapped);
   else if (OP == OP_RESET) env_reset(w, a.B, a.keys, env, lane);
   else if (OP == OP_FORWARD) env_forward(w, a.B, env, lane);
@@ -141,7 +171,7 @@ static void warp_entry(void* p, int lane) {
 #endif
 
 struct pgtt_env {
-  int device, N;
+  int device, N, wpb;
   ModelConst mc;
   EnvBuffers B;
   std::vector<void*> allocs;
@@ -182,14 +212,15 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
   a.B = e->B;
 #ifndef PGTT_HOST_EMU
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = (e->N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  const size_t smem = WARPS_PER_BLOCK * WS_BYTES;
+  const int wpb = e->wpb;
+  const int blocks = (e->N + wpb - 1) / wpb;
+  const size_t smem = wpb * WS_BYTES;
   switch (a.op) {
-    case OP_STEP: pgtt_env_kernel<OP_STEP><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a); break;
-    case OP_RESET: pgtt_env_kernel<OP_RESET><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a); break;
-    case OP_FORWARD: pgtt_env_kernel<OP_FORWARD><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a); break;
-    case OP_SCAN: pgtt_env_kernel<OP_SCAN><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a); break;
-    default: pgtt_env_kernel<OP_DEBUG><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a); break;
+    case OP_STEP: pgtt_env_kernel<OP_STEP><<<blocks, wpb * 32, smem, st>>>(a); break;
+    case OP_RESET: pgtt_env_kernel<OP_RESET><<<blocks, wpb * 32, smem, st>>>(a); break;
+    case OP_FORWARD: pgtt_env_kernel<OP_FORWARD><<<blocks, wpb * 32, smem, st>>>(a); break;
+    case OP_SCAN: pgtt_env_kernel<OP_SCAN><<<blocks, wpb * 32, smem, st>>>(a); break;
+    default: pgtt_env_kernel<OP_DEBUG><<<blocks, wpb * 32, smem, st>>>(a); break;
   }
   CUDA_OK(cudaGetLastError());
 #else
@@ -238,7 +269,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
     if (ce != cudaSuccess || ndev == 0) return fail(PGTT_ERR_CUDA, std::string("pgtt_create: no CUDA device: ") + cudaGetErrorString(ce));
     if (device < 0 || device >= ndev) return fail(PGTT_ERR_ARG, "pgtt_create: bad device index");
     CUDA_OK(cudaSetDevice(device));
-    const size_t smem = WARPS_PER_BLOCK * WS_BYTES;
+    const size_t smem = MAX_WARPS_PER_BLOCK * WS_BYTES;
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -247,7 +278,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   }
 #endif
   pgtt_env* e = new pgtt_env();
-  e->device = device; e->N = num_envs; e->terrain_dev = nullptr; e->n_terrains = 0; e->launches = 0; e->randomized = false;
+  e->device = device; e->N = num_envs; e->wpb = pick_warps_per_block(num_envs); e->terrain_dev = nullptr; e->n_terrains = 0; e->launches = 0; e->randomized = false;
   ModelConst& c = e->mc;
   memset(&c, 0, sizeof(c));
   c.dt = (float)m->timestep; c.gravity_z = (float)m->gravity[2]; c.impratio = (float)m->impratio;

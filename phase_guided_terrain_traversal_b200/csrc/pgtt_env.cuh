@@ -13,7 +13,8 @@
 struct Key { uint32_t a, b; };
 
 DEV uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
-DEV Key threefry(Key k, uint32_t x0, uint32_t x1) {
+// noinline: ~170 instructions, called from ~25 sites of the obs / command / reset code
+DEV_NOINLINE Key threefry(Key k, uint32_t x0, uint32_t x1) {
   const uint32_t ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
   x0 += ks0; x1 += ks1;
 #define TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }
@@ -186,13 +187,13 @@ DEV void write_obs(WS& w, const EnvBuffers& B, int env, Key& rng, const float* p
 
 // history rolls of _get_obs (joystick_pgtt.py:319-334), `step` is info["step"] BEFORE the increment
 DEV void update_history(WS& w, const EnvBuffers& B, int env, int step, const float* motor_targets, int lane) {
-  if (step % GC.history_update_steps != 0) return;
+  const bool upd = (step % GC.history_update_steps == 0) && lane < 12;
   float* qv = B.qvel_hist + (size_t)env * 24;
   float* qe = B.qpos_err_hist + (size_t)env * 24;
   float a = 0.f, b = 0.f;
-  if (lane < 12) { a = qv[lane]; b = qe[lane]; }
+  if (upd) { a = qv[lane]; b = qe[lane]; }
   syncwarp();
-  if (lane < 12) {
+  if (upd) {
     qv[12 + lane] = a; qe[12 + lane] = b;
     qv[lane] = w.qvel[6 + lane];
     qe[lane] = w.qpos[7 + lane] - motor_targets[lane];

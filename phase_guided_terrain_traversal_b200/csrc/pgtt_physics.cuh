@@ -143,7 +143,7 @@ DEV void kinematics(WS& w, int lane) {
     const float* o = GC.foot_pos;
     for (int i = 0; i < 3; i++) w.foot[g][i] = p[i] + R[3 * i] * o[0] + R[3 * i + 1] * o[1] + R[3 * i + 2] * o[2];
   }
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 DEV void com_inertia_cdof(WS& w, int lane) {
@@ -197,7 +197,7 @@ DEV void com_inertia_cdof(WS& w, int lane) {
       cross3(cd + 3, ax, off);
     }
   }
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 DEV void crb_and_inertia(WS& w, int lane) {
@@ -233,7 +233,7 @@ DEV void crb_and_inertia(WS& w, int lane) {
       w.MA[e3] = v;
     }
   }
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 // y = M x with the arrow blocks (x, y in shared memory; caller syncs)
@@ -393,7 +393,7 @@ DEV void velocity_rne(WS& w, int lane) {
     tot[i] = v + fb[i];
   }
   if (lane < 6) w.bias[lane] = dot6(w.cdof[lane], tot);
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 // passive + actuator + bias -> qfrc_smooth; leaves actuator_force in w.actf
@@ -411,7 +411,7 @@ DEV void smooth_forces(WS& w, int lane) {
     }
     w.qs[d] = f;
   }
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -455,6 +455,102 @@ DEV float sphere_box_local(const float* bx, const float* p, float r, float* l, f
   return sqrtf(e0 * e0 + e1 * e1 + e2 * e2) - r;
 }
 
+DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
+  const float r = GC.foot_r;
+  const int nb = GC.n_boxes;
+  int ncand = 0;
+  // bounding-sphere distances of all 4 x 100 pairs; scratch aliases the inertia workspace, which is
+  // only filled after the collision stage (forward() runs collision right after kinematics)
+  float* bs = &w.cinert[0][0];
+  const unsigned lt = (1u << lane) - 1u;
+  const float r2 = r * r * 1.0001f;  // conservative pre-filter; the exact test runs only where it passes
+#pragma unroll 1
+  for (int it = 0; it < 4; it++) {
+    const int k = it * 32 + lane;
+    const bool valid = k < nb;
+    const float* bx = w.box[valid ? k : 0];
+    const float4 b0 = *reinterpret_cast<const float4*>(bx), b1 = *reinterpret_cast<const float4*>(bx + 4);
+#pragma unroll 1
+    for (int f = 0; f < 4; f++) {
+      const float dx = b0.x - w.foot[f][0], dy = b0.y - w.foot[f][1], dz = b0.z - w.foot[f][2];
+      const float bsd = sqrtf(dx * dx + dy * dy + dz * dz) - (r + GC.box_rbound);
+      if (valid) bs[f * NBOX + k] = bsd;
+      const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
+      const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
+      const bool maybe = valid && (e0 * e0 + e1 * e1 + e2 * e2 < r2);
+      if (any_lane(maybe)) {
+        float l[3], pt[3];
+        const float dist = maybe ? sphere_box_local(bx, w.foot[f], r, l, pt) : 1.f;
+        const bool hit = maybe && dist < 0.f;
+        const unsigned m = wballot(hit);
+        if (hit) {
+          const int idx = ncand + popc(m & lt);
+          if (idx < MAXCAND) { w.cand_pair[idx] = f * NBOX + k; w.cand_dist[idx] = dist; w.cand_cd2[idx] = bsd; }
+        }
+        ncand += popc(m);
+      }
+    }
+  }
+  if (ncand > MAXCAND) ncand = MAXCAND;
+  syncwarp();
+  if (ncand == 0) return;
+  // broad-phase rank of every penetrating pair among all 4*nb pairs (keep the max_geom_pairs nearest
+  // centres); lane c ends up owning candidate c
+  const bool cull = (GC.max_geom_pairs > -1) && (4 * nb > GC.max_geom_pairs);
+  int mycnt = 0;
+  if (cull) {
+#pragma unroll 1
+    for (int c = 0; c < ncand; c++) {
+      int cnt = 0;
+      const float t = w.cand_cd2[c];
+      const int pi = w.cand_pair[c];
+#pragma unroll 1
+      for (int f = 0; f < 4; f++)
+#pragma unroll 1
+        for (int k = lane; k < nb; k += 32) {
+          const float v = bs[f * NBOX + k];
+          const int id = f * NBOX + k;
+          cnt += (v < t) || (v == t && id < pi);
+        }
+      cnt = warp_sum_i(cnt);
+      if (lane == c) mycnt = cnt;
+    }
+  }
+  // keep the max_contact_points deepest of the surviving pairs (ties -> broad-phase order, then slot order)
+  const float inf = __int_as_float(0x7f800000);
+  const bool mine = lane < ncand && !(cull && mycnt >= GC.max_geom_pairs);
+  float myd = mine ? w.cand_dist[lane] : inf;
+  const int mypair = w.cand_pair[lane < ncand ? lane : 0];
+  const int maxc = GC.max_contact_points < 4 ? GC.max_contact_points : 4;
+#pragma unroll 1
+  for (int s = 0; s < maxc; s++) {
+    const float dmin = warp_min(myd);
+    if (all_lanes(dmin == inf)) break;
+    const bool tie = (myd == dmin);
+    const int cm = warp_min_i(tie ? mycnt : 0x7fffffff);
+    const unsigned win = wballot(tie && mycnt == cm);
+    if (lane == ffs_(win) - 1) {
+      const int c = 4 + s, f = mypair / NBOX, k = mypair % NBOX;
+      const float* bx = w.box[k];
+      float l[3], pt[3];
+      const float dist = sphere_box_local(bx, w.foot[f], r, l, pt);
+      float nl[3] = {pt[0] - l[0], pt[1] - l[1], pt[2] - l[2]};
+      const float dn = sqrtf(dot3(nl, nl));
+      if (dn < PGTT_MINVAL) { nl[0] = nl[1] = nl[2] = 0.f; } else { nl[0] /= dn; nl[1] /= dn; nl[2] /= dn; }
+      // contact point: midway between the box point and the sphere surface point
+      const float pl0 = 0.5f * (pt[0] + l[0] + nl[0] * r), pl1 = 0.5f * (pt[1] + l[1] + nl[1] * r), pl2 = 0.5f * (pt[2] + l[2] + nl[2] * r);
+      float nw[3] = {bx[6] * nl[0] - bx[7] * nl[1], bx[7] * nl[0] + bx[6] * nl[1], nl[2]};
+      w.c_pos[c][0] = bx[0] + bx[6] * pl0 - bx[7] * pl1;
+      w.c_pos[c][1] = bx[1] + bx[7] * pl0 + bx[6] * pl1;
+      w.c_pos[c][2] = bx[2] + pl2;
+      make_frame(w.c_frame[c], nw);
+      w.c_dist[c] = dist; w.c_leg[c] = f; w.c_box[c] = k;
+      w.c_mu[c] = fmaxf(GC.foot_mu, B.m_boxfric[env * NBOX + k]);
+      myd = inf;
+    }
+  }
+}
+
 DEV void collision(WS& w, const EnvBuffers& B, int env, int lane) {
   const float r = GC.foot_r;
   if (lane < 4) {
@@ -469,94 +565,8 @@ DEV void collision(WS& w, const EnvBuffers& B, int env, int lane) {
     w.c_dist[lane] = 1.f; w.c_leg[lane] = 0; w.c_box[lane] = -2;  // empty slot
   }
   const int nb = GC.n_boxes;
-  if (nb <= 0) { syncwarp(); return; }
-  int ncand = 0;
-  float bs[4][4];  // bounding-sphere distance of (iteration, foot) for this lane's boxes
-  const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int it = 0; it < 4; it++) {
-    const int k = it * 32 + lane;
-    const bool valid = k < nb;
-    const float* bx = w.box[valid ? k : 0];
-#pragma unroll
-    for (int f = 0; f < 4; f++) {
-      float l[3], pt[3];
-      const float dist = sphere_box_local(bx, w.foot[f], r, l, pt);
-      const float dx = bx[0] - w.foot[f][0], dy = bx[1] - w.foot[f][1], dz = bx[2] - w.foot[f][2];
-      bs[it][f] = sqrtf(dx * dx + dy * dy + dz * dz) - (r + GC.box_rbound);
-      const bool hit = valid && dist < 0.f;
-      const unsigned m = wballot(hit);
-      if (m) {
-        if (hit) {
-          const int idx = ncand + popc(m & lt);
-          if (idx < MAXCAND) { w.cand_pair[idx] = f * NBOX + k; w.cand_dist[idx] = dist; w.cand_cd2[idx] = bs[it][f]; }
-        }
-        ncand += popc(m);
-      }
-    }
-  }
-  if (ncand > MAXCAND) ncand = MAXCAND;
-  syncwarp();
-  if (ncand == 0) return;
-  // broad-phase rank of every penetrating pair among all 4*nb pairs (keep the max_geom_pairs nearest centres)
-  const bool cull = (GC.max_geom_pairs > -1) && (4 * nb > GC.max_geom_pairs);
-  for (int c = 0; c < ncand; c++) {
-    int cnt = 0;
-    if (cull) {
-      const float t = w.cand_cd2[c];
-      const int pi = w.cand_pair[c];
-#pragma unroll
-      for (int it = 0; it < 4; it++) {
-        const int k = it * 32 + lane;
-        if (k < nb)
-#pragma unroll
-          for (int f = 0; f < 4; f++) {
-            const int id = f * NBOX + k;
-            cnt += (bs[it][f] < t) || (bs[it][f] == t && id < pi);
-          }
-      }
-      cnt = warp_sum_i(cnt);
-    }
-    if (lane == 0) w.cand_cnt[c] = cnt;
-  }
-  syncwarp();
-  // keep the max_contact_points deepest of the surviving pairs (ties -> broad-phase order)
-  int sel[4] = {-1, -1, -1, -1};
-  unsigned used = 0;
-  const int maxc = GC.max_contact_points < 4 ? GC.max_contact_points : 4;
-  for (int s = 0; s < maxc; s++) {
-    int best = -1;
-    for (int c = 0; c < ncand; c++) {
-      if ((used >> c) & 1u) continue;
-      if (cull && w.cand_cnt[c] >= GC.max_geom_pairs) continue;
-      if (best < 0 || w.cand_dist[c] < w.cand_dist[best] ||
-          (w.cand_dist[c] == w.cand_dist[best] && w.cand_cnt[c] < w.cand_cnt[best]))
-        best = c;
-    }
-    if (best < 0) break;
-    used |= 1u << best;
-    sel[s] = best;
-  }
-  syncwarp();
-  if (lane < 4 && sel[lane] >= 0) {
-    const int c = 4 + lane, pr = w.cand_pair[sel[lane]], f = pr / NBOX, k = pr % NBOX;
-    const float* bx = w.box[k];
-    float l[3], pt[3];
-    const float dist = sphere_box_local(bx, w.foot[f], r, l, pt);
-    float nl[3] = {pt[0] - l[0], pt[1] - l[1], pt[2] - l[2]};
-    const float dn = sqrtf(dot3(nl, nl));
-    if (dn < PGTT_MINVAL) { nl[0] = nl[1] = nl[2] = 0.f; } else { nl[0] /= dn; nl[1] /= dn; nl[2] /= dn; }
-    // contact point: midway between the box point and the sphere surface point
-    const float pl0 = 0.5f * (pt[0] + l[0] + nl[0] * r), pl1 = 0.5f * (pt[1] + l[1] + nl[1] * r), pl2 = 0.5f * (pt[2] + l[2] + nl[2] * r);
-    float nw[3] = {bx[6] * nl[0] - bx[7] * nl[1], bx[7] * nl[0] + bx[6] * nl[1], nl[2]};
-    w.c_pos[c][0] = bx[0] + bx[6] * pl0 - bx[7] * pl1;
-    w.c_pos[c][1] = bx[1] + bx[7] * pl0 + bx[6] * pl1;
-    w.c_pos[c][2] = bx[2] + pl2;
-    make_frame(w.c_frame[c], nw);
-    w.c_dist[c] = dist; w.c_leg[c] = f; w.c_box[c] = k;
-    w.c_mu[c] = fmaxf(GC.foot_mu, B.m_boxfric[env * NBOX + k]);
-  }
-  syncwarp();
+  if (nb > 0) collide_boxes(w, B, env, lane);
+  stage_sync(w.bar_threads);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -570,6 +580,11 @@ struct Rows {
   int lactive;
 };
 
+// impedance curve for a general solimp power (never taken by the GO2 model: power = 2)
+DEV_NOINLINE float imp_curve_general(float x, float mid, float power) {
+  return x < mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
+
 DEV void kbi(const float* solref, const float* solimp, float pos, float* k, float* b, float* imp) {
   float timeconst = fmaxf(solref[0], 2.f * GC.dt);
   const float dampratio = solref[1];
@@ -579,10 +594,9 @@ DEV void kbi(const float* solref, const float* solimp, float pos, float* k, floa
   *k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
   *b = 2.f / (dmax * timeconst);
   const float x = fabsf(pos) / width;
-  float ia, ib;
-  if (power == 2.f) { ia = x * x / mid; ib = 1.f - (1.f - x) * (1.f - x) / (1.f - mid); }
-  else { ia = powf(x, power) / powf(mid, power - 1.f); ib = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f); }
-  const float y = x < mid ? ia : ib;
+  float y;
+  if (power == 2.f) y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  else y = imp_curve_general(x, mid, power);
   float im = dmin + y * (dmax - dmin);
   im = fminf(fmaxf(im, dmin), dmax);
   if (x > 1.f) im = dmax;
@@ -660,7 +674,7 @@ DEV void make_rows(WS& w, Rows& R, int lane) {
     for (int c = 0; c < NCON; c++) if ((m >> (4 * c)) & 1u) w.actlist[n++] = c;
     w.nact = n;
   }
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -789,7 +803,7 @@ DEV void linesearch(WS& w, Rows& R, const SolveState& S, int lane) {
     done |= (!swap) && (it > 0);
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
-    if (done) break;
+    if (all_lanes(done)) break;
     const LSPoint lo_next = ls_eval(lo.alpha - lo.d0 / lo.d1, R, q, lq, qg);
     const LSPoint hi_next = ls_eval(hi.alpha - hi.d0 / hi.d1, R, q, lq, qg);
     const LSPoint mid = ls_eval(0.5f * (lo.alpha + hi.alpha), R, q, lq, qg);
@@ -835,7 +849,7 @@ DEV int solve(WS& w, Rows& R, int lane) {
   ctx_init(w, R, w.qas, lane);
   update_constraint(w, R, S, false, lane);
   const float cost_smooth = S.cost;
-  if (cost_warm < cost_smooth) ctx_init(w, R, w.warm, lane);
+  if (all_lanes(cost_warm < cost_smooth)) ctx_init(w, R, w.warm, lane);
   S.cost = __int_as_float(0x7f800000);  // +inf
   S.prev_cost = 0.f;
   update_constraint(w, R, S, true, lane);
@@ -849,7 +863,7 @@ DEV int solve(WS& w, Rows& R, int lane) {
     bool done = niter >= GC.iterations;
     done |= improvement < GC.tolerance;
     done |= gradient < GC.tolerance;
-    if (done && GC.iterations != 1) break;
+    if (all_lanes(done) && GC.iterations != 1) break;
     linesearch(w, R, S, lane);
     update_constraint(w, R, S, true, lane);
     update_gradient(w, R, F, lane);
@@ -857,7 +871,7 @@ DEV int solve(WS& w, Rows& R, int lane) {
     if (GC.iterations == 1) break;
   }
   if (lane < NV) w.warm[lane] = w.qacc[lane];
-  syncwarp();
+  stage_sync(w.bar_threads);
   return niter;
 }
 
@@ -912,7 +926,7 @@ DEV void sensors(WS& w, int lane) {
       w.sens[3 + i] = (R[i] * aw0 + R[3 + i] * aw1 + R[6 + i] * aw2) + corr[i];
     }
   }
-  syncwarp();
+  stage_sync(w.bar_threads);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -920,9 +934,9 @@ DEV void sensors(WS& w, int lane) {
 // ----------------------------------------------------------------------------------------------
 DEV int forward(WS& w, const EnvBuffers& B, int env, int lane, bool with_sensors) {
   kinematics(w, lane);
+  collision(w, B, env, lane);   // before the inertia stages: its scratch aliases w.cinert
   com_inertia_cdof(w, lane);
   crb_and_inertia(w, lane);
-  collision(w, B, env, lane);
   velocity_rne(w, lane);
   smooth_forces(w, lane);
   Rows R;
@@ -932,6 +946,7 @@ DEV int forward(WS& w, const EnvBuffers& B, int env, int lane, bool with_sensors
     arrow_factor(w, w.MB, w.MC, w.MA, F, lane);
     arrow_solve(w, F, w.qs, w.qas, lane);
   }
+  stage_sync(w.bar_threads);
   const int niter = solve(w, R, lane);
   if (with_sensors) sensors(w, lane);
   return niter;
@@ -957,5 +972,5 @@ DEV void euler(WS& w, int lane) {
     const float rn = 1.0f / sqrtf(rw * rw + rx * rx + ry * ry + rz * rz);
     w.qpos[3] = rw * rn; w.qpos[4] = rx * rn; w.qpos[5] = ry * rn; w.qpos[6] = rz * rn;
   } else if (lane >= 6 && lane < NV) w.qpos[lane + 1] += dt * w.qvel[lane];
-  syncwarp();
+  stage_sync(w.bar_threads);
 }

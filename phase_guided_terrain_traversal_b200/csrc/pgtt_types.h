@@ -103,4 +103,5 @@ struct WS {
   float scan[NRAY];
   float sens[NSENSOR];
   int niter[4];
+  int bar_threads;  // threads of this CTA that take part in stage barriers (32 x live warps)
 };

@@ -21,11 +21,23 @@ DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
 DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
 DEV unsigned wballot(bool p) { return __ballot_sync(FULL_MASK, p); }
 DEV bool any_lane(bool p) { return __any_sync(FULL_MASK, p); }
+// Control decisions go through a vote so that the compiler knows the branch is warp-uniform; a
+// branch on a butterfly-reduced float is uniform in fact but not provably, and every shuffle
+// behind it is then emitted as an out-of-line WARPSYNC.COLLECTIVE trampoline.
+DEV bool all_lanes(bool p) { return __all_sync(FULL_MASK, p); }
 DEV void syncwarp() { __syncwarp(); }
+// Stage barrier across the warps (= envs) of a CTA. Envs are independent, so this is not needed for
+// correctness beyond the warp-level ordering it implies; it keeps the warps of a CTA streaming
+// through the same stretch of code so instruction-cache lines are fetched once per CTA, not once per warp.
+DEV void stage_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+DEV int warp_index() { return __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0); }
 DEV float ldg(const float* p) { return __ldg(p); }
 DEV int popc(unsigned x) { return __popc(x); }
+DEV int ffs_(unsigned x) { return __ffs((int)x); }
 DEV float rsqrt_(float x) { return rsqrtf(x); }
-DEV void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+// one out-of-line copy of the accurate sincosf (its range-reduction slow path is ~100 instructions per inlined site)
+DEV_NOINLINE float2 sincos2_(float a) { float2 r; sincosf(a, &r.x, &r.y); return r; }
+DEV void sincos_(float a, float* s, float* c) { const float2 r = sincos2_(a); *s = r.x; *c = r.y; }
 // un-contracted multiply-add: random draws must not depend on whether the compiler forms an FMA
 DEV float mul_add_nofma(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
 #endif
@@ -38,6 +50,11 @@ DEV float warp_sum(float v) {
 DEV int warp_sum_i(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += shfl_xor(v, o);
+  return v;
+}
+DEV int warp_min_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int u = shfl_xor(v, o); v = u < v ? u : v; }
   return v;
 }
 DEV float warp_max(float v) {

@@ -74,9 +74,12 @@ DEV unsigned wballot(bool pr) {
   return r;
 }
 DEV bool any_lane(bool p) { return wballot(p) != 0; }
+DEV bool all_lanes(bool p) { return wballot(p) == FULL_MASK; }
 DEV void syncwarp() { emu_barrier(); }
+DEV void stage_sync(int) { emu_barrier(); }
 DEV float ldg(const float* p) { return *p; }
 DEV int popc(unsigned x) { return __builtin_popcount(x); }
+DEV int ffs_(unsigned x) { return __builtin_ffs((int)x); }
 DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
 DEV void sincos_(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
 DEV float mul_add_nofma(float a, float b, float c) { return a * b + c; }  // built with -ffp-contract=off
