@@ -141,27 +141,34 @@ DEV void heightscan(WS& w, const float* center, float yaw, float* out, int* boxl
 // ----------------------------------------------------------------------------------------------
 DEV void write_obs(WS& w, const EnvBuffers& B, int env, Key& rng, const float* phase, float gait_freq, const float* last_act,
                    const float* command, const int* last_contact, const float* feet_air_time, int lane) {
-  Key nk[5];
+  // five sequential (rng, key) = split(rng) of _get_obs: the rng chain is computed by every lane, but a
+  // lane derives only the noise key of its own slot group (and the height-scan key), so the number of
+  // threefry evaluations per lane is 5 + 1 + 1 + 1 + 4 instead of 10 + 4 + 4
+  Key chain[5];
 #pragma unroll
-  for (int s = 0; s < 5; s++) { nk[s] = rng_split(rng, 2, 1); rng = rng_split(rng, 2, 0); }
+  for (int s = 0; s < 5; s++) { chain[s] = rng; rng = rng_split(rng, 2, 0); }
   float* o = B.obs_state + (size_t)env * NOBS;
   float* pr = B.obs_priv + (size_t)env * NPRIV;
   const float lvl = GC.noise_level;
   const float* R = w.xmat[0];
-  float v = 0.f;
-  int slot = -1;
-  if (lane < 3) { slot = lane; v = w.sens[lane] + (2.f * rng_unit(nk[0], 3, lane) - 1.f) * lvl * GC.noise_gyro; }
-  else if (lane < 6) {
-    const int i = lane - 3;
-    slot = lane; v = -R[6 + i] + (2.f * rng_unit(nk[1], 3, i) - 1.f) * lvl * GC.noise_gravity;  // xmat^T (0,0,-1)
-  } else if (lane < 18) {
-    const int i = lane - 6;
-    slot = lane; v = (w.qpos[7 + i] + (2.f * rng_unit(nk[2], 12, i) - 1.f) * lvl * GC.noise_joint_pos) - GC.default_pose[i];
-  } else if (lane < 30) {
-    const int i = lane - 18;
-    slot = lane; v = w.qvel[6 + i] + (2.f * rng_unit(nk[3], 12, i) - 1.f) * lvl * GC.noise_joint_vel;
+  {
+    // slot group of this lane: gyro 0..2 | gravity 3..5 | joint pos 6..17 | joint vel 18..29
+    const int grp = lane < 3 ? 0 : (lane < 6 ? 1 : (lane < 18 ? 2 : 3));
+    const int idx = lane < 3 ? lane : (lane < 6 ? lane - 3 : (lane < 18 ? lane - 6 : lane - 18));
+    const int cnt = grp < 2 ? 3 : 12;
+    Key base = chain[0];
+    if (grp == 1) base = chain[1];
+    if (grp == 2) base = chain[2];
+    if (grp == 3) base = chain[3];
+    const float u = 2.f * rng_unit(rng_split(base, 2, 1), cnt, idx < cnt ? idx : 0) - 1.f;
+    float v = 0.f;
+    if (lane < 3) v = w.sens[lane] + u * lvl * GC.noise_gyro;
+    else if (lane < 6) v = -R[6 + idx] + u * lvl * GC.noise_gravity;                       // xmat^T (0,0,-1)
+    else if (lane < 18) v = (w.qpos[7 + idx] + u * lvl * GC.noise_joint_pos) - GC.default_pose[idx];
+    else if (lane < 30) v = w.qvel[6 + idx] + u * lvl * GC.noise_joint_vel;
+    if (lane < 30) { o[lane] = v; pr[lane] = v; }
   }
-  if (slot >= 0) { o[slot] = v; pr[slot] = v; }
+  const Key scan_key = rng_split(chain[4], 2, 1);   // the linvel key, re-used for the height scan (Q9)
   if (lane < 4) {
     float s, c;
     sincos_(phase[lane], &s, &c);
@@ -171,7 +178,7 @@ DEV void write_obs(WS& w, const EnvBuffers& B, int env, Key& rng, const float* p
   for (int r = lane; r < NRAY; r += 32) zmin = fminf(zmin, w.scan[r]);
   zmin = warp_min(zmin);
   for (int r = lane; r < NRAY; r += 32) {
-    const float z = (w.scan[r] - zmin) + (2.f * rng_unit(nk[4], NRAY, r) - 1.f) * lvl * GC.noise_heightscan;
+    const float z = (w.scan[r] - zmin) + (2.f * rng_unit(scan_key, NRAY, r) - 1.f) * lvl * GC.noise_heightscan;
     o[38 + r] = z; pr[38 + r] = z;
   }
   if (lane == 0) { o[155] = gait_freq; pr[155] = gait_freq; }
@@ -371,9 +378,10 @@ DEV void env_step(WS& w, const EnvBuffers& B, const float* action_all, int env, 
   if (lane < NU) { B.last_last_act[env * NU + lane] = last_act; B.last_act[env * NU + lane] = action; }
   if (lane < 4) B.phase[env * 4 + lane] = fmodf(phase + B.phase_dt[env], 2.f * PGTT_PI);
   int steps_until = B.steps_until[env] - 1;
-  const Key key1 = rng_split(rng, 3, 1), key2 = rng_split(rng, 3, 2);
+  const Key rng3 = rng;   // rng, key1, key2 = split(rng, 3): key1 / key2 are derived only when consumed
   rng = rng_split(rng, 3, 0);
   if (steps_until <= 0) {  // sample_command (joystick_pgtt.py:603-611)
+    const Key key1 = rng_split(rng3, 3, 1);
     const Key y_rng = rng_split(key1, 4, 1), w_rng = rng_split(key1, 4, 2), z_rng = rng_split(key1, 4, 3);
     if (lane < 3) {
       const float y = rng_uniform(y_rng, 3, lane, GC.cmd_u_min[lane], GC.cmd_u_max[lane]);
@@ -382,7 +390,7 @@ DEV void env_step(WS& w, const EnvBuffers& B, const float* action_all, int env, 
       B.command[env * 3 + lane] = command - ww * (command - y * z);
     }
   }
-  if (done || steps_until <= 0) steps_until = (int)rintf(-log1pf(-rng_unit(key2, 1, 0)) * 5.0f / dt);
+  if (done || steps_until <= 0) steps_until = (int)rintf(-log1pf(-rng_unit(rng_split(rng3, 3, 2), 1, 0)) * 5.0f / dt);
   float sp_mean = 0.f;
   if (lane < 4) {
     air *= (float)(!contact);

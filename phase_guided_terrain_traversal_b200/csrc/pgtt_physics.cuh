@@ -464,28 +464,36 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
   float* bs = &w.cinert[0][0];
   const unsigned lt = (1u << lane) - 1u;
   const float r2 = r * r * 1.0001f;  // conservative pre-filter; the exact test runs only where it passes
+  float ft[4][3];
+#pragma unroll
+  for (int f = 0; f < 4; f++) { ft[f][0] = w.foot[f][0]; ft[f][1] = w.foot[f][1]; ft[f][2] = w.foot[f][2]; }
 #pragma unroll 1
   for (int it = 0; it < 4; it++) {
     const int k = it * 32 + lane;
     const bool valid = k < nb;
     const float* bx = w.box[valid ? k : 0];
     const float4 b0 = *reinterpret_cast<const float4*>(bx), b1 = *reinterpret_cast<const float4*>(bx + 4);
-#pragma unroll 1
+    unsigned maybe = 0u;
+#pragma unroll
     for (int f = 0; f < 4; f++) {
-      const float dx = b0.x - w.foot[f][0], dy = b0.y - w.foot[f][1], dz = b0.z - w.foot[f][2];
-      const float bsd = sqrtf(dx * dx + dy * dy + dz * dz) - (r + GC.box_rbound);
-      if (valid) bs[f * NBOX + k] = bsd;
+      const float dx = b0.x - ft[f][0], dy = b0.y - ft[f][1], dz = b0.z - ft[f][2];
+      // broad-phase key: squared centre distance (same order as mjx's |d| - (r + rbound): rbound is one constant)
+      if (valid) bs[f * NBOX + k] = dx * dx + dy * dy + dz * dz;
       const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
       const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
-      const bool maybe = valid && (e0 * e0 + e1 * e1 + e2 * e2 < r2);
-      if (any_lane(maybe)) {
+      if (valid && (e0 * e0 + e1 * e1 + e2 * e2 < r2)) maybe |= 1u << f;
+    }
+    if (any_lane(maybe != 0u)) {
+#pragma unroll 1
+      for (int f = 0; f < 4; f++) {
+        const bool mb = (maybe >> f) & 1u;
         float l[3], pt[3];
-        const float dist = maybe ? sphere_box_local(bx, w.foot[f], r, l, pt) : 1.f;
-        const bool hit = maybe && dist < 0.f;
+        const float dist = mb ? sphere_box_local(bx, w.foot[f], r, l, pt) : 1.f;
+        const bool hit = mb && dist < 0.f;
         const unsigned m = wballot(hit);
         if (hit) {
           const int idx = ncand + popc(m & lt);
-          if (idx < MAXCAND) { w.cand_pair[idx] = f * NBOX + k; w.cand_dist[idx] = dist; w.cand_cd2[idx] = bsd; }
+          if (idx < MAXCAND) { w.cand_pair[idx] = f * NBOX + k; w.cand_dist[idx] = dist; w.cand_cd2[idx] = bs[f * NBOX + k]; }
         }
         ncand += popc(m);
       }
@@ -711,6 +719,7 @@ DEV void update_constraint(WS& w, Rows& R, SolveState& S, bool need_force, int l
     w.Ac[c][0] = wn; w.Ac[c][1] = mu * wd; w.Ac[c][2] = mu * wd2; w.Ac[c][3] = mu * mu * ws; w.Ac[c][4] = mu * mu * ws2;
   }
   const float lf = lact ? R.lsign * R.lD * -R.ljaref : 0.f;
+  if (lane < 12) w.limD[lane] = lact ? R.lD : 0.f;   // Hessian diagonal of the joint-limit rows
   syncwarp();
   if (lane < NV) {
     float s = 0.f;
@@ -725,49 +734,87 @@ DEV void update_constraint(WS& w, Rows& R, SolveState& S, bool need_force, int l
   }
   syncwarp();
   if (lane < 12) w.qfc[6 + lane] += lf;
-  R.jv = (float)act;       // stash the active flags for update_gradient
-  R.ljv = (float)lact;
   syncwarp();
 }
 
-DEV void update_gradient(WS& w, Rows& R, ArrowFac& F, int lane) {
+// element (row ci, column cj) of the 9x9 contact-local Hessian block that this lane accumulates:
+// e in [0,36) -> base block, [36,54) -> base x leg coupling, [54,63) -> leg block
+DEV void hess_elem(int e, int* ci, int* cj) {
+  if (e < 36) { *ci = e / 6; *cj = e % 6; }
+  else if (e < 54) { *ci = (e - 36) / 3; *cj = 6 + (e - 36) % 3; }
+  else { *ci = 6 + (e - 54) / 3; *cj = 6 + (e - 54) % 3; }
+}
+
+// gradient, Hessian H = M + J^T diag(D active) J in arrow form, Newton direction.
+// Each lane accumulates two fixed elements of the contact-local 9x9 blocks in registers over the
+// active contacts (leg-dependent destinations get one accumulator per leg), then writes H once.
+DEV void update_gradient(WS& w, int lane) {
   if (lane < NV) w.grad[lane] = w.Ma[lane] - w.qs[lane] - w.qfc[lane];
-  for (int e = lane; e < 144; e += 32) {
-    if (e < 36) w.HB[e] = w.MB[e];
-    else if (e < 108) w.HC[e - 36] = w.MC[e - 36];
-    else w.HA[e - 108] = w.MA[e - 108];
-  }
-  syncwarp();
-  if (lane < 12 && R.ljv != 0.f) w.HA[(lane / 3) * 9 + (lane % 3) * 4] += R.lD;
-  syncwarp();
-  for (int i = 0; i < w.nact; i++) {
+  const int e1 = lane + 32;
+  int ci0, cj0, ci1, cj1;
+  hess_elem(lane, &ci0, &cj0);
+  hess_elem(e1 < 63 ? e1 : 62, &ci1, &cj1);
+  float acc0 = 0.f, accb = 0.f, accl[4] = {0.f, 0.f, 0.f, 0.f};
+  const int nact = w.nact;
+#pragma unroll 1
+  for (int i = 0; i < nact; i++) {
     const int c = w.actlist[i], leg = w.c_leg[c];
     const float A0 = w.Ac[c][0], A1 = w.Ac[c][1], A2 = w.Ac[c][2], A3 = w.Ac[c][3], A4 = w.Ac[c][4];
-    for (int e = lane; e < 63; e += 32) {
-      int ci, cj; float* dst;
-      if (e < 36) { ci = e / 6; cj = e % 6; dst = &w.HB[e]; }
-      else if (e < 54) { const int e2 = e - 36; ci = e2 / 3; cj = 6 + e2 % 3; dst = &w.HC[leg * 18 + e2]; }
-      else { const int e3 = e - 54; ci = 6 + e3 / 3; cj = 6 + e3 % 3; dst = &w.HA[leg * 9 + e3]; }
-      const float j0 = w.Jc[c][0][cj], j1 = w.Jc[c][1][cj], j2 = w.Jc[c][2][cj];
+    {
+      const float j0 = w.Jc[c][0][cj0], j1 = w.Jc[c][1][cj0], j2 = w.Jc[c][2][cj0];
       const float g0 = A0 * j0 + A1 * j1 + A2 * j2, g1 = A1 * j0 + A3 * j1, g2 = A2 * j0 + A4 * j2;
-      *dst += w.Jc[c][0][ci] * g0 + w.Jc[c][1][ci] * g1 + w.Jc[c][2][ci] * g2;
+      acc0 += w.Jc[c][0][ci0] * g0 + w.Jc[c][1][ci0] * g1 + w.Jc[c][2][ci0] * g2;
+    }
+    {
+      const float j0 = w.Jc[c][0][cj1], j1 = w.Jc[c][1][cj1], j2 = w.Jc[c][2][cj1];
+      const float g0 = A0 * j0 + A1 * j1 + A2 * j2, g1 = A1 * j0 + A3 * j1, g2 = A2 * j0 + A4 * j2;
+      const float v = w.Jc[c][0][ci1] * g0 + w.Jc[c][1][ci1] * g1 + w.Jc[c][2][ci1] * g2;
+      accb += v;
+#pragma unroll
+      for (int g = 0; g < 4; g++) accl[g] += (leg == g) ? v : 0.f;
     }
   }
+  w.HB[lane] = w.MB[lane] + acc0;
+  if (e1 < 36) w.HB[e1] = w.MB[e1] + accb;
+  else if (e1 < 54) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) w.HC[g * 18 + (e1 - 36)] = w.MC[g * 18 + (e1 - 36)] + accl[g];
+  } else if (e1 < 63) {
+    const int e3 = e1 - 54, j = e3 / 3;
+    const bool diag = (e3 % 3) == j;
+#pragma unroll
+    for (int g = 0; g < 4; g++) w.HA[g * 9 + e3] = w.MA[g * 9 + e3] + accl[g] + (diag ? w.limD[3 * g + j] : 0.f);
+  }
   syncwarp();
+  ArrowFac F;
   arrow_factor(w, w.HB, w.HC, w.HA, F, lane);
   arrow_solve(w, F, w.grad, w.search, lane);
   if (lane < NV) w.search[lane] = -w.search[lane];
   syncwarp();
 }
 
-// evaluate cost / derivatives of the 1-D restriction at alpha (quadratics held per row in registers)
+// 1-D restriction of the cost along the search direction: cost / derivatives at alpha. Per-row
+// quadratics live in registers; their sum over the rows active at alpha only depends on the active
+// SET, so the butterfly sums are cached per (contact-row mask, limit-row mask) - most evaluations of
+// one line search see the set of alpha = 0 or of the Newton step. Cached sums are the identical
+// butterfly results, so caching does not change a single bit.
 struct LSPoint { float alpha, cost, d0, d1; };
+struct LSCache { unsigned m[2], lm[2]; float s[2][3]; };
 
-DEV LSPoint ls_eval(float alpha, const Rows& R, const float* q, const float* lq, const float* qg) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  if (R.active && (R.jaref + alpha * R.jv < 0.f)) { s0 += q[0]; s1 += q[1]; s2 += q[2]; }
-  if (R.lactive && (R.ljaref + alpha * R.ljv < 0.f)) { s0 += lq[0]; s1 += lq[1]; s2 += lq[2]; }
-  s0 = warp_sum(s0) + qg[0]; s1 = warp_sum(s1) + qg[1]; s2 = warp_sum(s2) + qg[2];
+DEV LSPoint ls_eval(float alpha, const Rows& R, const float* q, const float* lq, const float* qg, LSCache& C, int lane) {
+  const unsigned m = wballot(R.active && (R.jaref + alpha * R.jv < 0.f));
+  const unsigned lm = wballot(R.lactive && (R.ljaref + alpha * R.ljv < 0.f));
+  float s0, s1, s2;
+  if (m == C.m[0] && lm == C.lm[0]) { s0 = C.s[0][0]; s1 = C.s[0][1]; s2 = C.s[0][2]; }
+  else if (m == C.m[1] && lm == C.lm[1]) { s0 = C.s[1][0]; s1 = C.s[1][1]; s2 = C.s[1][2]; }
+  else {
+    const bool on = (m >> lane) & 1u, lon = (lm >> lane) & 1u;
+    s0 = 0.f; s1 = 0.f; s2 = 0.f;
+    if (on) { s0 += q[0]; s1 += q[1]; s2 += q[2]; }
+    if (lon) { s0 += lq[0]; s1 += lq[1]; s2 += lq[2]; }
+    s0 = warp_sum(s0) + qg[0]; s1 = warp_sum(s1) + qg[1]; s2 = warp_sum(s2) + qg[2];
+    C.m[1] = m; C.lm[1] = lm; C.s[1][0] = s0; C.s[1][1] = s1; C.s[1][2] = s2;
+  }
   LSPoint p;
   p.alpha = alpha;
   p.cost = alpha * alpha * s2 + alpha * s1 + s0;
@@ -792,21 +839,31 @@ DEV void linesearch(WS& w, Rows& R, const SolveState& S, int lane) {
   const float qg[3] = {S.gauss, b, 0.5f * c2};
   const float q[3] = {0.5f * R.jaref * R.jaref * R.D, R.jv * R.jaref * R.D, 0.5f * R.jv * R.jv * R.D};
   const float lq[3] = {0.5f * R.ljaref * R.ljaref * R.lD, R.ljv * R.ljaref * R.lD, 0.5f * R.ljv * R.ljv * R.lD};
-  const LSPoint p0 = ls_eval(0.f, R, q, lq, qg);
-  const LSPoint l0 = ls_eval(p0.alpha - p0.d0 / p0.d1, R, q, lq, qg);
+  LSCache C;
+  {  // prime both cache entries with the alpha = 0 active set
+    const unsigned m = wballot(R.active && (R.jaref < 0.f)), lm = wballot(R.lactive && (R.ljaref < 0.f));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if ((m >> lane) & 1u) { s0 += q[0]; s1 += q[1]; s2 += q[2]; }
+    if ((lm >> lane) & 1u) { s0 += lq[0]; s1 += lq[1]; s2 += lq[2]; }
+    s0 = warp_sum(s0) + qg[0]; s1 = warp_sum(s1) + qg[1]; s2 = warp_sum(s2) + qg[2];
+    for (int t = 0; t < 2; t++) { C.m[t] = m; C.lm[t] = lm; C.s[t][0] = s0; C.s[t][1] = s1; C.s[t][2] = s2; }
+  }
+  const LSPoint p0 = ls_eval(0.f, R, q, lq, qg, C, lane);
+  const LSPoint l0 = ls_eval(p0.alpha - p0.d0 / p0.d1, R, q, lq, qg, C, lane);
   const bool lesser = l0.d0 < p0.d0;
   LSPoint hi = lesser ? p0 : l0, lo = lesser ? l0 : p0;
   bool swap = true;
   int it = 0;
+#pragma unroll 1
   for (;;) {
     bool done = it >= GC.ls_iterations;
     done |= (!swap) && (it > 0);
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (all_lanes(done)) break;
-    const LSPoint lo_next = ls_eval(lo.alpha - lo.d0 / lo.d1, R, q, lq, qg);
-    const LSPoint hi_next = ls_eval(hi.alpha - hi.d0 / hi.d1, R, q, lq, qg);
-    const LSPoint mid = ls_eval(0.5f * (lo.alpha + hi.alpha), R, q, lq, qg);
+    const LSPoint lo_next = ls_eval(lo.alpha - lo.d0 / lo.d1, R, q, lq, qg, C, lane);
+    const LSPoint hi_next = ls_eval(hi.alpha - hi.d0 / hi.d1, R, q, lq, qg, C, lane);
+    const LSPoint mid = ls_eval(0.5f * (lo.alpha + hi.alpha), R, q, lq, qg, C, lane);
     const bool s_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (s_lo_next) lo = lo_next;
     const bool s_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
@@ -840,22 +897,24 @@ DEV void ctx_init(WS& w, Rows& R, const float* x, int lane) {
 
 DEV int solve(WS& w, Rows& R, int lane) {
   SolveState S;
-  ArrowFac F;
   // warm start: whichever of qacc_warmstart / qacc_smooth has the lower cost
   S.cost = 0.f; S.prev_cost = 0.f;
-  ctx_init(w, R, w.warm, lane);
-  update_constraint(w, R, S, false, lane);
-  const float cost_warm = S.cost;
-  ctx_init(w, R, w.qas, lane);
-  update_constraint(w, R, S, false, lane);
-  const float cost_smooth = S.cost;
-  if (all_lanes(cost_warm < cost_smooth)) ctx_init(w, R, w.warm, lane);
+  float c2[2];
+#pragma unroll 1
+  for (int t = 0; t < 2; t++) {
+    ctx_init(w, R, t == 0 ? w.warm : w.qas, lane);
+    update_constraint(w, R, S, false, lane);
+    c2[t] = S.cost;
+  }
+  if (all_lanes(c2[0] < c2[1])) ctx_init(w, R, w.warm, lane);
   S.cost = __int_as_float(0x7f800000);  // +inf
   S.prev_cost = 0.f;
-  update_constraint(w, R, S, true, lane);
-  update_gradient(w, R, F, lane);
   int niter = 0;
+#pragma unroll 1
   for (;;) {
+    update_constraint(w, R, S, true, lane);
+    update_gradient(w, lane);
+    if (niter > 0 && GC.iterations == 1) break;
     const float improvement = (S.prev_cost - S.cost) / GC.solver_scale;
     float gn = lane < NV ? w.grad[lane] * w.grad[lane] : 0.f;
     gn = warp_sum(gn);
@@ -865,10 +924,7 @@ DEV int solve(WS& w, Rows& R, int lane) {
     done |= gradient < GC.tolerance;
     if (all_lanes(done) && GC.iterations != 1) break;
     linesearch(w, R, S, lane);
-    update_constraint(w, R, S, true, lane);
-    update_gradient(w, R, F, lane);
     niter++;
-    if (GC.iterations == 1) break;
   }
   if (lane < NV) w.warm[lane] = w.qacc[lane];
   stage_sync(w.bar_threads);

@@ -95,7 +95,7 @@ struct WS {
   // contacts: slots 0..3 = foot g vs floor, 4..7 = selected foot-box contacts
   int c_leg[NCON], c_box[NCON];
   float c_dist[NCON], c_pos[NCON][3], c_frame[NCON][9], c_mu[NCON];
-  float Jc[NCON][3][9], Ac[NCON][6], fc[NCON][3];
+  float Jc[NCON][3][9], Ac[NCON][6], fc[NCON][3], limD[12];
   int nact, actlist[NCON];
   int cand_n, cand_pair[MAXCAND], cand_cnt[MAXCAND];
   float cand_dist[MAXCAND], cand_cd2[MAXCAND];
