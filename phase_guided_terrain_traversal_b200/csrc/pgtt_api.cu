@@ -65,11 +65,8 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
   smooth_forces(w, lane);
   Rows R;
   make_rows(w, R, lane);
-  {
-    ArrowFac F;
-    arrow_factor(w, w.MB, w.MC, w.MA, F, lane);
-    arrow_solve(w, F, w.qs, w.qas, lane);
-  }
+  arrow_factor(w, w.MB, w.MC, w.MA, lane);
+  arrow_solve(w, w.qs, w.qas, lane);
   for (int i = lane; i < 39; i += 32) { o[DBG_XPOS + i] = (&w.xpos[0][0])[i]; o[DBG_XIPOS + i] = (&w.xipos[0][0])[i]; }
   for (int i = lane; i < 117; i += 32) o[DBG_XMAT + i] = (&w.xmat[0][0])[i];
   if (lane < 3) o[DBG_COM + lane] = w.com[lane];
@@ -284,6 +281,8 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   c.dt = (float)m->timestep; c.gravity_z = (float)m->gravity[2]; c.impratio = (float)m->impratio;
   c.tolerance = (float)m->tolerance; c.ls_tolerance = (float)m->ls_tolerance; c.meaninertia = (float)m->meaninertia;
   c.solver_scale = (float)(m->meaninertia * NV);
+  c.sync_mask = 0x7ff;
+  if (const char* sm = getenv("PGTT_SYNC_MASK")) c.sync_mask = (int)strtol(sm, nullptr, 0);
   c.iterations = m->iterations; c.ls_iterations = m->ls_iterations; c.max_geom_pairs = m->max_geom_pairs;
   c.max_contact_points = m->max_contact_points; c.n_boxes = m->n_boxes; c.n_substeps = t->n_substeps;
   for (int b = 0; b < NB; b++) {

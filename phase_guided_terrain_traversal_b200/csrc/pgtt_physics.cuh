@@ -22,6 +22,13 @@ __constant__ ModelConst g_mc;
 #endif
 #define GC g_mc
 
+// stage barrier ids (bit positions of ModelConst::sync_mask)
+enum { ST_KIN = 0, ST_COLLIDE, ST_COM, ST_CRB, ST_RNE, ST_SMOOTH, ST_ROWS, ST_PRESOLVE, ST_POSTSOLVE, ST_SENSORS, ST_EULER };
+// CTA barrier after stage `id` if enabled (see simt.h:cta_bar), else just the warp-level sync the stage needs
+DEV void stage_sync(const WS& w, int id) {
+  if ((GC.sync_mask >> id) & 1) cta_bar(w.bar_threads); else syncwarp();
+}
+
 #define PGTT_MINVAL 1e-15f
 #define PGTT_PI 3.14159265358979323846f
 
@@ -143,7 +150,7 @@ DEV void kinematics(WS& w, int lane) {
     const float* o = GC.foot_pos;
     for (int i = 0; i < 3; i++) w.foot[g][i] = p[i] + R[3 * i] * o[0] + R[3 * i + 1] * o[1] + R[3 * i + 2] * o[2];
   }
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_KIN);
 }
 
 DEV void com_inertia_cdof(WS& w, int lane) {
@@ -197,7 +204,7 @@ DEV void com_inertia_cdof(WS& w, int lane) {
       cross3(cd + 3, ax, off);
     }
   }
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_COM);
 }
 
 DEV void crb_and_inertia(WS& w, int lane) {
@@ -233,7 +240,7 @@ DEV void crb_and_inertia(WS& w, int lane) {
       w.MA[e3] = v;
     }
   }
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_CRB);
 }
 
 // y = M x with the arrow blocks (x, y in shared memory; caller syncs)
@@ -261,7 +268,9 @@ struct ArrowFac {
   float la[6];  // Cholesky of this lane's leg block: i00 l10 i11 l20 l21 i22 (reciprocal diagonals)
 };
 
-DEV void arrow_factor(WS& w, const float* Bm, const float* Cm, const float* Am, ArrowFac& F, int lane) {
+// Factor lives in shared memory (w.fLA, w.fY, w.fL) so it can be re-used by later solves.
+DEV void arrow_factor(WS& w, const float* Bm, const float* Cm, const float* Am, int lane) {
+  ArrowFac F;
   const int g = lane >> 3, sub = lane & 7;
   const float* Ag = Am + 9 * g;
   const float i00 = rsqrt_(fmaxf(Ag[0], PGTT_MINVAL));
@@ -296,12 +305,27 @@ DEV void arrow_factor(WS& w, const float* Bm, const float* Cm, const float* Am, 
       F.L[idx++] = (i == j) ? rsqrt_(fmaxf(s, PGTT_MINVAL)) : s * F.L[j * (j + 1) / 2 + j];
     }
   }
+  if (lane < 21) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 21; k++) v = (lane == k) ? F.L[k] : v;
+    w.fL[lane] = v;
+  }
+  if (sub == 6) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) w.fLA[g][k] = F.la[k];
+  }
   syncwarp();
 }
 
 // x = H^-1 r  (r, x in shared memory, may alias). Ends with a syncwarp.
-DEV void arrow_solve(WS& w, const ArrowFac& F, const float* r, float* x, int lane) {
+DEV void arrow_solve(WS& w, const float* r, float* x, int lane) {
   const int g = lane >> 3, sub = lane & 7;
+  ArrowFac F;
+#pragma unroll
+  for (int k = 0; k < 21; k++) F.L[k] = w.fL[k];
+#pragma unroll
+  for (int k = 0; k < 6; k++) F.la[k] = w.fLA[g][k];
   const float r0 = r[6 + 3 * g], r1 = r[7 + 3 * g], r2 = r[8 + 3 * g];
   float t = 0.f;
   if (sub < 6) t = w.fY[g][sub][0] * r0 + w.fY[g][sub][1] * r1 + w.fY[g][sub][2] * r2;
@@ -393,7 +417,7 @@ DEV void velocity_rne(WS& w, int lane) {
     tot[i] = v + fb[i];
   }
   if (lane < 6) w.bias[lane] = dot6(w.cdof[lane], tot);
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_RNE);
 }
 
 // passive + actuator + bias -> qfrc_smooth; leaves actuator_force in w.actf
@@ -411,7 +435,7 @@ DEV void smooth_forces(WS& w, int lane) {
     }
     w.qs[d] = f;
   }
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_SMOOTH);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -574,7 +598,7 @@ DEV void collision(WS& w, const EnvBuffers& B, int env, int lane) {
   }
   const int nb = GC.n_boxes;
   if (nb > 0) collide_boxes(w, B, env, lane);
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_COLLIDE);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -682,13 +706,13 @@ DEV void make_rows(WS& w, Rows& R, int lane) {
     for (int c = 0; c < NCON; c++) if ((m >> (4 * c)) & 1u) w.actlist[n++] = c;
     w.nact = n;
   }
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_ROWS);
 }
 
 // ----------------------------------------------------------------------------------------------
 // Newton solver with mjx's bracketed line search (App. A7)
 // ----------------------------------------------------------------------------------------------
-struct SolveState { float cost, prev_cost, gauss; };
+struct SolveState { float cost, prev_cost, gauss; unsigned am, lam, fac_am, fac_lam; bool fac_valid; };
 
 // jaref already holds J*qacc - aref in R; w.Ma = M*qacc. Computes forces, qfc, cost.
 DEV void update_constraint(WS& w, Rows& R, SolveState& S, bool need_force, int lane) {
@@ -704,6 +728,7 @@ DEV void update_constraint(WS& w, Rows& R, SolveState& S, bool need_force, int l
   S.prev_cost = S.cost;
   S.cost = 0.5f * cpart + S.gauss;
   if (!need_force) return;
+  S.am = wballot(act); S.lam = wballot(lact);
   // contact-space force and Hessian weights per contact, gathered inside each 4-lane group
   const float f = act ? R.D * -R.jaref : 0.f;
   const float wgt = act ? R.D : 0.f;
@@ -745,50 +770,54 @@ DEV void hess_elem(int e, int* ci, int* cj) {
   else { *ci = 6 + (e - 54) / 3; *cj = 6 + (e - 54) % 3; }
 }
 
-// gradient, Hessian H = M + J^T diag(D active) J in arrow form, Newton direction.
+// Newton direction: Hessian H = M + J^T diag(D active) J in arrow form, factor, solve.
 // Each lane accumulates two fixed elements of the contact-local 9x9 blocks in registers over the
 // active contacts (leg-dependent destinations get one accumulator per leg), then writes H once.
-DEV void update_gradient(WS& w, int lane) {
-  if (lane < NV) w.grad[lane] = w.Ma[lane] - w.qs[lane] - w.qfc[lane];
-  const int e1 = lane + 32;
-  int ci0, cj0, ci1, cj1;
-  hess_elem(lane, &ci0, &cj0);
-  hess_elem(e1 < 63 ? e1 : 62, &ci1, &cj1);
-  float acc0 = 0.f, accb = 0.f, accl[4] = {0.f, 0.f, 0.f, 0.f};
-  const int nact = w.nact;
+// H only depends on the active set (J, D are fixed within a solve), so the factor of the previous
+// iteration is re-used bit for bit when the set did not change.
+DEV void newton_direction(WS& w, SolveState& S, int lane) {
+  syncwarp();   // w.grad was just written by lanes < NV
+  if (!(S.fac_valid && S.am == S.fac_am && S.lam == S.fac_lam)) {
+    const int e1 = lane + 32;
+    int ci0, cj0, ci1, cj1;
+    hess_elem(lane, &ci0, &cj0);
+    hess_elem(e1 < 63 ? e1 : 62, &ci1, &cj1);
+    float acc0 = 0.f, accb = 0.f, accl[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nact = w.nact;
 #pragma unroll 1
-  for (int i = 0; i < nact; i++) {
-    const int c = w.actlist[i], leg = w.c_leg[c];
-    const float A0 = w.Ac[c][0], A1 = w.Ac[c][1], A2 = w.Ac[c][2], A3 = w.Ac[c][3], A4 = w.Ac[c][4];
-    {
-      const float j0 = w.Jc[c][0][cj0], j1 = w.Jc[c][1][cj0], j2 = w.Jc[c][2][cj0];
-      const float g0 = A0 * j0 + A1 * j1 + A2 * j2, g1 = A1 * j0 + A3 * j1, g2 = A2 * j0 + A4 * j2;
-      acc0 += w.Jc[c][0][ci0] * g0 + w.Jc[c][1][ci0] * g1 + w.Jc[c][2][ci0] * g2;
+    for (int i = 0; i < nact; i++) {
+      const int c = w.actlist[i], leg = w.c_leg[c];
+      const float A0 = w.Ac[c][0], A1 = w.Ac[c][1], A2 = w.Ac[c][2], A3 = w.Ac[c][3], A4 = w.Ac[c][4];
+      {
+        const float j0 = w.Jc[c][0][cj0], j1 = w.Jc[c][1][cj0], j2 = w.Jc[c][2][cj0];
+        const float g0 = A0 * j0 + A1 * j1 + A2 * j2, g1 = A1 * j0 + A3 * j1, g2 = A2 * j0 + A4 * j2;
+        acc0 += w.Jc[c][0][ci0] * g0 + w.Jc[c][1][ci0] * g1 + w.Jc[c][2][ci0] * g2;
+      }
+      {
+        const float j0 = w.Jc[c][0][cj1], j1 = w.Jc[c][1][cj1], j2 = w.Jc[c][2][cj1];
+        const float g0 = A0 * j0 + A1 * j1 + A2 * j2, g1 = A1 * j0 + A3 * j1, g2 = A2 * j0 + A4 * j2;
+        const float v = w.Jc[c][0][ci1] * g0 + w.Jc[c][1][ci1] * g1 + w.Jc[c][2][ci1] * g2;
+        accb += v;
+#pragma unroll
+        for (int g = 0; g < 4; g++) accl[g] += (leg == g) ? v : 0.f;
+      }
     }
-    {
-      const float j0 = w.Jc[c][0][cj1], j1 = w.Jc[c][1][cj1], j2 = w.Jc[c][2][cj1];
-      const float g0 = A0 * j0 + A1 * j1 + A2 * j2, g1 = A1 * j0 + A3 * j1, g2 = A2 * j0 + A4 * j2;
-      const float v = w.Jc[c][0][ci1] * g0 + w.Jc[c][1][ci1] * g1 + w.Jc[c][2][ci1] * g2;
-      accb += v;
+    w.HB[lane] = w.MB[lane] + acc0;
+    if (e1 < 36) w.HB[e1] = w.MB[e1] + accb;
+    else if (e1 < 54) {
 #pragma unroll
-      for (int g = 0; g < 4; g++) accl[g] += (leg == g) ? v : 0.f;
+      for (int g = 0; g < 4; g++) w.HC[g * 18 + (e1 - 36)] = w.MC[g * 18 + (e1 - 36)] + accl[g];
+    } else if (e1 < 63) {
+      const int e3 = e1 - 54, j = e3 / 3;
+      const bool diag = (e3 % 3) == j;
+#pragma unroll
+      for (int g = 0; g < 4; g++) w.HA[g * 9 + e3] = w.MA[g * 9 + e3] + accl[g] + (diag ? w.limD[3 * g + j] : 0.f);
     }
+    syncwarp();
+    arrow_factor(w, w.HB, w.HC, w.HA, lane);
+    S.fac_valid = true; S.fac_am = S.am; S.fac_lam = S.lam;
   }
-  w.HB[lane] = w.MB[lane] + acc0;
-  if (e1 < 36) w.HB[e1] = w.MB[e1] + accb;
-  else if (e1 < 54) {
-#pragma unroll
-    for (int g = 0; g < 4; g++) w.HC[g * 18 + (e1 - 36)] = w.MC[g * 18 + (e1 - 36)] + accl[g];
-  } else if (e1 < 63) {
-    const int e3 = e1 - 54, j = e3 / 3;
-    const bool diag = (e3 % 3) == j;
-#pragma unroll
-    for (int g = 0; g < 4; g++) w.HA[g * 9 + e3] = w.MA[g * 9 + e3] + accl[g] + (diag ? w.limD[3 * g + j] : 0.f);
-  }
-  syncwarp();
-  ArrowFac F;
-  arrow_factor(w, w.HB, w.HC, w.HA, F, lane);
-  arrow_solve(w, F, w.grad, w.search, lane);
+  arrow_solve(w, w.grad, w.search, lane);
   if (lane < NV) w.search[lane] = -w.search[lane];
   syncwarp();
 }
@@ -909,25 +938,29 @@ DEV int solve(WS& w, Rows& R, int lane) {
   if (all_lanes(c2[0] < c2[1])) ctx_init(w, R, w.warm, lane);
   S.cost = __int_as_float(0x7f800000);  // +inf
   S.prev_cost = 0.f;
+  S.fac_valid = false;
   int niter = 0;
 #pragma unroll 1
   for (;;) {
+    // mjx order is constraint update -> gradient + Newton direction -> convergence test; the direction
+    // is only consumed by the next line search, so it is computed after the test (same results)
     update_constraint(w, R, S, true, lane);
-    update_gradient(w, lane);
+    float gn = 0.f;
+    if (lane < NV) { const float gr = w.Ma[lane] - w.qs[lane] - w.qfc[lane]; w.grad[lane] = gr; gn = gr * gr; }
     if (niter > 0 && GC.iterations == 1) break;
     const float improvement = (S.prev_cost - S.cost) / GC.solver_scale;
-    float gn = lane < NV ? w.grad[lane] * w.grad[lane] : 0.f;
     gn = warp_sum(gn);
     const float gradient = sqrtf(gn) / GC.solver_scale;
     bool done = niter >= GC.iterations;
     done |= improvement < GC.tolerance;
     done |= gradient < GC.tolerance;
     if (all_lanes(done) && GC.iterations != 1) break;
+    newton_direction(w, S, lane);
     linesearch(w, R, S, lane);
     niter++;
   }
   if (lane < NV) w.warm[lane] = w.qacc[lane];
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_POSTSOLVE);
   return niter;
 }
 
@@ -982,7 +1015,7 @@ DEV void sensors(WS& w, int lane) {
       w.sens[3 + i] = (R[i] * aw0 + R[3 + i] * aw1 + R[6 + i] * aw2) + corr[i];
     }
   }
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_SENSORS);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -997,12 +1030,9 @@ DEV int forward(WS& w, const EnvBuffers& B, int env, int lane, bool with_sensors
   smooth_forces(w, lane);
   Rows R;
   make_rows(w, R, lane);
-  {
-    ArrowFac F;
-    arrow_factor(w, w.MB, w.MC, w.MA, F, lane);
-    arrow_solve(w, F, w.qs, w.qas, lane);
-  }
-  stage_sync(w.bar_threads);
+  arrow_factor(w, w.MB, w.MC, w.MA, lane);
+  arrow_solve(w, w.qs, w.qas, lane);
+  stage_sync(w, ST_PRESOLVE);
   const int niter = solve(w, R, lane);
   if (with_sensors) sensors(w, lane);
   return niter;
@@ -1028,5 +1058,5 @@ DEV void euler(WS& w, int lane) {
     const float rn = 1.0f / sqrtf(rw * rw + rx * rx + ry * ry + rz * rz);
     w.qpos[3] = rw * rn; w.qpos[4] = rx * rn; w.qpos[5] = ry * rn; w.qpos[6] = rz * rn;
   } else if (lane >= 6 && lane < NV) w.qpos[lane + 1] += dt * w.qvel[lane];
-  stage_sync(w.bar_threads);
+  stage_sync(w, ST_EULER);
 }

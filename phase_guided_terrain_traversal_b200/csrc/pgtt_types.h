@@ -24,6 +24,7 @@
 struct ModelConst {
   float dt, gravity_z, impratio, tolerance, ls_tolerance, meaninertia, solver_scale;
   int iterations, ls_iterations, max_geom_pairs, max_contact_points, n_boxes, n_substeps;
+  int sync_mask;   // which stages end in a CTA barrier (tuning knob, pgtt_api.cu)
   float body_pos[NB][3], body_ipos[NB][3], body_I[NB][6];  // body-frame inertia tensor xx yy zz xy xz yz
   float jnt_lo[12], jnt_hi[12], dof_invw[12], calf_invw[4];
   float lim_solref[2], lim_solimp[5];
@@ -88,6 +89,7 @@ struct WS {
   float fLA[NLEG][6];       // Cholesky of A_g: l00 l10 l11 l20 l21 l22 (diagonals stored as reciprocals)
   float fY[NLEG][6][3];     // C_g A_g^-1
   float fS[36];             // Schur complement of the base block
+  float fL[24];             // its Cholesky factor, row-packed lower, diagonals as reciprocals (21 used)
   float tb[6];
   // vectors
   float bias[NV], qs[NV], qas[NV], Ma[NV], grad[NV], search[NV], mv[NV], qfc[NV];

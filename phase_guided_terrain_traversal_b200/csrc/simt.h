@@ -29,7 +29,7 @@ DEV void syncwarp() { __syncwarp(); }
 // Stage barrier across the warps (= envs) of a CTA. Envs are independent, so this is not needed for
 // correctness beyond the warp-level ordering it implies; it keeps the warps of a CTA streaming
 // through the same stretch of code so instruction-cache lines are fetched once per CTA, not once per warp.
-DEV void stage_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+DEV void cta_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 DEV int warp_index() { return __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0); }
 DEV float ldg(const float* p) { return __ldg(p); }
 DEV int popc(unsigned x) { return __popc(x); }

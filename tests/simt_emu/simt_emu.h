@@ -76,7 +76,7 @@ DEV unsigned wballot(bool pr) {
 DEV bool any_lane(bool p) { return wballot(p) != 0; }
 DEV bool all_lanes(bool p) { return wballot(p) == FULL_MASK; }
 DEV void syncwarp() { emu_barrier(); }
-DEV void stage_sync(int) { emu_barrier(); }
+DEV void cta_bar(int) { emu_barrier(); }
 DEV float ldg(const float* p) { return *p; }
 DEV int popc(unsigned x) { return __builtin_popcount(x); }
 DEV int ffs_(unsigned x) { return __builtin_ffs((int)x); }
