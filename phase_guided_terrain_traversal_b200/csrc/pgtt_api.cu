@@ -281,7 +281,9 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   c.dt = (float)m->timestep; c.gravity_z = (float)m->gravity[2]; c.impratio = (float)m->impratio;
   c.tolerance = (float)m->tolerance; c.ls_tolerance = (float)m->ls_tolerance; c.meaninertia = (float)m->meaninertia;
   c.solver_scale = (float)(m->meaninertia * NV);
-  c.sync_mask = 0x7ff;
+  // CTA barriers after collision, before and after the Newton solver: the stages whose duration varies
+  // between envs; in between the warps of a CTA stay aligned by themselves (measured: profiles/r01b)
+  c.sync_mask = (1 << ST_COLLIDE) | (1 << ST_PRESOLVE) | (1 << ST_POSTSOLVE);
   if (const char* sm = getenv("PGTT_SYNC_MASK")) c.sync_mask = (int)strtol(sm, nullptr, 0);
   c.iterations = m->iterations; c.ls_iterations = m->ls_iterations; c.max_geom_pairs = m->max_geom_pairs;
   c.max_contact_points = m->max_contact_points; c.n_boxes = m->n_boxes; c.n_substeps = t->n_substeps;
