@@ -58,6 +58,8 @@ def _lib(precision: str):
         lib.orc_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         lib.orc_set.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         lib.orc_field_count.argtypes = [ctypes.c_char_p]
+        lib.orc_ray.restype = ctypes.c_double
+        lib.orc_ray.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         lib.orc_get_contacts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         lib.orc_rng_split.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.orc_rng_uniform.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
@@ -175,6 +177,10 @@ class Oracle:
         out = np.zeros((self.n, 117, 3))
         self.lib.orc_scan(self.h, c.ctypes.data, y.ctypes.data, out.ctypes.data)
         return out.reshape(self.n, 13, 9, 3)
+
+    def ray(self, i: int, pnt, vec) -> float:
+        p = np.ascontiguousarray(pnt, dtype=np.float64); v = np.ascontiguousarray(vec, dtype=np.float64)
+        return float(self.lib.orc_ray(self.h, i, p.ctypes.data, v.ctypes.data))
 
     def contacts(self, i: int):
         f = np.zeros((8, 17))

@@ -1279,6 +1279,14 @@ void orc_scan(void* hv, const double* center, const double* yaw, double* out) { 
   }
 }
 
+/* mjx.ray(m, d, pnt, vec, geomgroup=(1,0,0,0,1,1)) for env i: distance to the nearest floor / box hit, -1 if none */
+double orc_ray(void* hv, int i, const double* pnt, const double* vec) {
+  Handle* h = (Handle*)hv;
+  real p[3] = {(real)pnt[0], (real)pnt[1], (real)pnt[2]}, v[3] = {(real)vec[0], (real)vec[1], (real)vec[2]};
+  real dist = ray_scene(&h->env[i].m, p, v);
+  return isinf((double)dist) ? -1.0 : (double)dist;
+}
+
 /* ---- field access by name: kind 0 = real, 1 = int32, 2 = uint32 ----------------------------- */
 typedef struct { const char* name; size_t off; int count; int kind; } Field;
 #define F_(name, member, cnt, kind) {name, offsetof(Env, member), cnt, kind}

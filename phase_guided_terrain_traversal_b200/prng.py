@@ -87,3 +87,50 @@ def as_keys(rng, num_envs: int | None = None, partitionable: bool = True) -> np.
     if num_envs is not None and a.shape[0] != num_envs:
         raise ValueError(f"got {a.shape[0]} keys for {num_envs} envs")
     return np.ascontiguousarray(a)
+
+
+# --------------------------------------------------------------------------------------------------
+# draws (host restatement of jax.random for tests / fixtures; the env draws on the device)
+# --------------------------------------------------------------------------------------------------
+def random_bits(key, n: int, partitionable: bool = True) -> np.ndarray:
+    """jax.random.bits(key, (n,), uint32)."""
+    key = np.asarray(key, dtype=np.uint32).reshape(2)
+    if partitionable:
+        a, b = threefry2x32(key, np.zeros(n, dtype=np.uint32), np.arange(n, dtype=np.uint32))
+        return a ^ b
+    half = (n + 1) // 2
+    cnt = np.arange(2 * half, dtype=np.uint32)
+    if n & 1:
+        cnt[-1] = 0  # odd sizes are zero-padded
+    a, b = threefry2x32(key, cnt[:half], cnt[half:])
+    return np.concatenate([a, b])[:n]
+
+
+def uniform(key, shape=(), minval=0.0, maxval=1.0, partitionable: bool = True) -> np.ndarray:
+    """jax.random.uniform(key, shape, float32, minval, maxval): mantissa trick, affine map, clamp at minval."""
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    n = int(np.prod(shape)) if shape else 1
+    bits = random_bits(key, n, partitionable)
+    u = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo = np.broadcast_to(np.asarray(minval, dtype=np.float32), shape).reshape(-1) if shape else np.asarray(minval, dtype=np.float32).reshape(-1)
+    hi = np.broadcast_to(np.asarray(maxval, dtype=np.float32), shape).reshape(-1) if shape else np.asarray(maxval, dtype=np.float32).reshape(-1)
+    v = np.maximum(lo, (u * (hi - lo) + lo).astype(np.float32))
+    return v.reshape(shape).astype(np.float32)
+
+
+def exponential(key, partitionable: bool = True) -> np.float32:
+    u = uniform(key, (), partitionable=partitionable)
+    return np.float32(-np.log1p(-u))
+
+
+def bernoulli(key, p, shape=(), partitionable: bool = True) -> np.ndarray:
+    return uniform(key, shape, partitionable=partitionable) < np.asarray(p, dtype=np.float32)
+
+
+def randint(key, minval: int, maxval: int, partitionable: bool = True) -> int:
+    """jax.random.randint(key, (), minval, maxval) for int32 (two 32-bit draws + modular combination)."""
+    k1, k2 = split(key, 2, partitionable)
+    hb, lb = int(random_bits(k1, 1, partitionable)[0]), int(random_bits(k2, 1, partitionable)[0])
+    span = max(maxval - minval, 1)
+    mult = ((65536 % span) * (65536 % span)) % span
+    return minval + ((hb % span) * mult + (lb % span)) % span

@@ -1,0 +1,126 @@
+"""Host-side mirror of the reference interface: configs, constants, registry, ABI surface, error behaviour.
+No compute calls here (no GPU): the C-ABI library is only loaded and its exports / error paths checked."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import phase_guided_terrain_traversal_b200 as pkg
+from phase_guided_terrain_traversal_b200 import _native as nat
+from phase_guided_terrain_traversal_b200 import prng, registry, terrain
+from phase_guided_terrain_traversal_b200.go2 import configs, go2_constants as consts
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+def _norm(x):
+    if isinstance(x, dict):
+        return {k: _norm(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_norm(v) for v in x]
+    return x
+
+
+def test_configs_equal_the_reference_factories():
+    """default_config() / baseline_config() key for key against go2/configs.py evaluated (tests/golden/make_golden.py)."""
+    ref = json.loads((GOLD / "reference_config.json").read_text())
+    assert _norm(configs.default_config().to_dict()) == ref["default_config"]
+    assert _norm(configs.baseline_config().to_dict()) == ref["baseline_config"]
+    # metrics / reward order is the dict order of the scales (go2/configs.py:31-59)
+    assert list(configs.default_config().reward_config.scales.keys()) == nat.REWARD_KEYS
+
+
+def test_constants_equal_the_reference():
+    ref = json.loads((GOLD / "reference_config.json").read_text())
+    for k, v in ref["constants"].items():
+        assert getattr(consts, k) == v, k
+    for t, p in ref["task_to_xml"].items():
+        assert consts.task_to_xml(t).as_posix() == p
+    with pytest.raises(KeyError):          # go2_constants.py:45-52 raises KeyError for an unknown task
+        consts.task_to_xml("rough_terrain_nonexistent")
+
+
+def test_training_overrides_match_train_py():
+    cfg = configs.training_overrides(configs.default_config())   # training/train.py:127-129
+    assert cfg.command_config.u_max == [0.6, 0.6, 1.0] and cfg.command_config.u_min == [-0.6, -0.6, -1.0] and cfg.gait_freq == [1, 3]
+
+
+def test_registry_call_sequence_of_train_py():
+    """register_environment -> get_default_config -> load -> _randomizer / get_domain_randomizer (train.py:116-130,165-170,231)."""
+    import functools
+    from phase_guided_terrain_traversal_b200.go2 import joystick_pgtt, randomize
+    registry.register_environment("Go2", functools.partial(joystick_pgtt.Joystick, task="stairs"), configs.default_config)
+    cfg = registry.get_default_config("Go2")
+    env = registry.load("Go2", config=configs.training_overrides(cfg))
+    assert env.action_size == 12 and env.dt == 0.02 and env.sim_dt == 0.005 and env.n_substeps == 4
+    assert env.observation_size == {"state": (171,), "privileged_state": (215,)}
+    assert env.xml_path.endswith("terrain_scene_mjx.xml") and env.mjx_model.n_boxes == 100
+    table = terrain.load_terrain("level1")
+    registry._randomizer["Go2"] = functools.partial(randomize.domain_randomize, terrain_matrix=table)
+    rm, in_axes = registry.get_domain_randomizer("Go2")(env.mjx_model, rng=prng.env_keys(0, 8))
+    assert rm.rng.shape == (8, 2) and rm.terrain_matrix.shape == (100, 100, 10) and in_axes["body_mass"] == 0
+    with pytest.raises(ValueError):
+        registry.load("NoSuchEnv")
+
+
+def test_abi_header_and_library_agree():
+    """Every function include/pgtt_b200.h declares is exported by the built library and listed in the binding."""
+    hdr = (ROOT / "include" / "pgtt_b200.h").read_text()
+    declared = set(re.findall(r"\b(pgtt_[a-z_0-9]+)\s*\(", hdr)) - {"pgtt_env"}
+    assert declared == set(nat.ABI_SYMBOLS), declared ^ set(nat.ABI_SYMBOLS)
+    nat.build_library()
+    try:
+        lib = ctypes.CDLL(str(nat.LIB_PATH))
+    except OSError as e:
+        pytest.skip(f"CUDA runtime not loadable on this host: {e}")
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert ctypes.sizeof(nat.Buffers) == 4 + 4 + 8 * len(nat.BUFFER_FIELDS)      # int + pad + pointers
+    lib = nat.declare(lib)
+    assert lib.pgtt_version() >= 100
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    """No CPU fallback: creating a handle on a machine without a CUDA device raises (PGTT_ERR_CUDA)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    env = Joystick(task="flat_terrain", config=configs.default_config())
+    with pytest.raises((nat.PgttError, nat.NativeLibraryError, RuntimeError, AssertionError)):
+        env.reset(prng.env_keys(0, 4))
+
+
+def test_missing_library_is_an_error(tmp_path):
+    with pytest.raises(nat.NativeLibraryError):
+        nat.load_library(tmp_path / "libpgtt_b200.so")
+
+
+def test_terrain_loader_and_fixture_invariants():
+    """terrains/level*.npy format: [T,100,10] f32, boxes stand on z = 0, yaw-only rotations."""
+    for name in ["level1", "level07", "level13"]:
+        t = terrain.load_terrain(name)
+        assert t.dtype == np.float32 and t.shape[1:] == (100, 10)
+        act = t[..., 0] < 50
+        assert np.allclose(t[act][:, 2], t[act][:, 9], atol=1e-6)
+        assert np.abs(t[..., 4:6]).max() == 0
+        terrain.validate_terrain(t)
+    with pytest.raises(FileNotFoundError):
+        terrain.load_terrain("level99")
+    with pytest.raises(ValueError):
+        from phase_guided_terrain_traversal_b200.go2.randomize import domain_randomize
+        domain_randomize(None, prng.env_keys(0, 2), np.zeros((3, 50, 10), np.float32))
+
+
+def test_key_helpers():
+    k = prng.as_keys(7, 5)
+    assert k.shape == (5, 2) and np.array_equal(k, prng.split(prng.PRNGKey(7), 5))
+    assert np.array_equal(prng.as_keys(k), k)
+    with pytest.raises(ValueError):
+        prng.as_keys(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        prng.as_keys(k, 6)
