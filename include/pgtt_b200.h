@@ -26,6 +26,7 @@
 #ifndef PGTT_B200_H
 #define PGTT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -150,6 +151,24 @@ int pgtt_debug_forward(pgtt_env* env, float* out, void* stream);
 
 /* Counters the bench reports: kernels launched by this handle since creation. */
 int64_t pgtt_launch_count(pgtt_env* env);
+
+/* ---- rollout collector: acting step of brax ppo (training/train.py:135-161,242-263; network spec as re-hosted by
+ * deploy/policy_net.py:35-64). One fused tcgen05 kernel: normalise obs -> MLP (swish) -> NormalTanh sample. ---- */
+typedef struct pgtt_policy pgtt_policy;
+const char* pgtt_policy_last_error(void);
+/* sizes[n_layers + 1] = {obs_dim, hidden..., 2 * act_dim}, e.g. {171, 512, 256, 128, 24} */
+int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy** out);
+int pgtt_policy_destroy(pgtt_policy* p);
+/* kernels[l]: HOST float [in][out] row-major (flax `kernel`), biases[l]: HOST float [out];
+ * obs_mean / obs_std: HOST float [obs_dim] (brax running statistics) or NULL for identity. */
+int pgtt_policy_set_params(pgtt_policy* p, const float* const* kernels, const float* const* biases, const float* obs_mean, const float* obs_std);
+/* obs DEVICE [n][obs_dim]. eps DEVICE [n][act_dim] or NULL (internal counter-based N(0,1) keyed by seed, step).
+ * Outputs DEVICE: action [n][act_dim] = tanh(raw); raw_action [n][act_dim], log_prob [n], logits [n][2 act_dim] may be NULL. */
+int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint64_t step, int deterministic, const float* eps,
+                    float* action, float* raw_action, float* log_prob, float* logits, void* stream);
+/* transition write-out: dst_base[slot][0..n_floats) <- src[0..n_floats) (both DEVICE) */
+int pgtt_store_slot(const float* src, float* dst_base, int slot, size_t n_floats, void* stream);
+int64_t pgtt_policy_launch_count(pgtt_policy* p);
 
 #ifdef __cplusplus
 }

@@ -185,12 +185,23 @@ def declare(lib):
     lib.pgtt_debug_forward.argtypes = [vp, vp, vp]
     lib.pgtt_launch_count.argtypes = [vp]
     lib.pgtt_launch_count.restype = C.c_int64
+    if hasattr(lib, "pgtt_policy_create"):     # absent from the host-emulated test library (env kernels only)
+        lib.pgtt_policy_last_error.restype = C.c_char_p
+        lib.pgtt_policy_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        lib.pgtt_policy_destroy.argtypes = [vp]
+        lib.pgtt_policy_set_params.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, vp]
+        lib.pgtt_policy_act.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
+        lib.pgtt_store_slot.argtypes = [vp, vp, C.c_int, C.c_size_t, vp]
+        lib.pgtt_policy_launch_count.argtypes = [vp]
+        lib.pgtt_policy_launch_count.restype = C.c_int64
     return lib
 
 
 ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
     "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_debug_forward", "pgtt_launch_count",
+    "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act", "pgtt_store_slot",
+    "pgtt_policy_launch_count",
 ]
 
 _LIB = None
@@ -198,12 +209,12 @@ _LIB = None
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """nvcc -> csrc/libpgtt_b200.so (in-tree, so it travels to the GPU box with the snapshot)."""
-    srcs = [CSRC / n for n in ("pgtt_api.cu", "pgtt_env.cuh", "pgtt_physics.cuh", "pgtt_types.h", "simt.h", "pgtt_debug.h")] + [INCLUDE / "pgtt_b200.h"]
+    srcs = [CSRC / n for n in ("pgtt_api.cu", "pgtt_policy.cu", "pgtt_env.cuh", "pgtt_physics.cuh", "pgtt_types.h", "simt.h", "pgtt_debug.h")] + [INCLUDE / "pgtt_b200.h"]
     newest = max(s.stat().st_mtime for s in srcs)
     if not force and LIB_PATH.exists() and LIB_PATH.stat().st_mtime >= newest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "pgtt_api.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "pgtt_api.cu"), str(CSRC / "pgtt_policy.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise NativeLibraryError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")

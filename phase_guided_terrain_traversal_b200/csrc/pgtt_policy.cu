@@ -1,0 +1,393 @@
+// pgtt_policy.cu - acting step of the PPO rollout collector on the 5th-gen tensor cores (sm_100a).
+//
+// Stands in for brax's `actor_step` as configured by training/train.py:135-161 (policy MLP
+// (512,256,128) on obs["state"], swish, NormalTanh distribution) and for deploy/policy_net.py:35-64
+// (same network re-hosted in torch): normalise obs -> 171->512->256->128->24 MLP -> loc | scale ->
+// raw = loc + (softplus(scale) + 0.001) * eps -> action = tanh(raw), log_prob.
+//
+// One CTA (128 threads) owns a tile of 128 envs and runs the WHOLE network for it in one launch:
+//   * activations live in shared memory as the K-major A operand (bf16, canonical no-swizzle UMMA layout),
+//   * weights are pre-packed on the host into the same canonical layout (B operand, K-chunks of <= 32 KB,
+//     double-buffered in shared memory),
+//   * `tcgen05.mma.cta_group::1.kind::f16` (M = 128, N <= 256, K = 16 per instruction) issued by one
+//     thread accumulates a whole layer in TMEM (fp32, up to 512 columns),
+//   * after `tcgen05.commit` -> mbarrier, the four warps read their 32 TMEM lanes with `tcgen05.ld`,
+//     apply bias + SiLU and write the next layer's A operand in place; the last layer's epilogue does
+//     the distribution math and writes action / raw_action / log_prob.
+// bf16 operands, fp32 accumulation (north-star: "policy MLP on tensor cores, bf16 in, fp32 accumulate").
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pgtt_b200.h"
+
+#define POL_TM 128            // envs per CTA = MMA M
+#define POL_MAXK 512          // widest activation
+#define POL_MAXLAYERS 6
+#define POL_BCHUNK 32768      // bytes per weight chunk buffer
+#define POL_A_BYTES (POL_TM * POL_MAXK * 2)
+#define POL_SMEM (POL_A_BYTES + 2 * POL_BCHUNK + 64)
+
+struct PolicyLayer {
+  int K, N, Kp, Np, Kc, nchunks;   // true sizes, padded sizes, K per chunk
+  size_t w_off, b_off;             // offsets (elements) into the packed weight / bias arrays
+};
+
+struct PolicyParams {
+  int n_layers, obs_dim, act_dim;
+  PolicyLayer L[POL_MAXLAYERS];
+  const __nv_bfloat16* w;   // packed chunks, canonical UMMA K-major layout
+  const float* bias;        // padded biases
+  const float* mean;        // [obs_dim]
+  const float* inv_std;     // [obs_dim]
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  // bounded spin: a protocol bug traps instead of hanging the GPU
+  for (long it = 0; it < (1L << 28); it++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address [0,14) >> 4 | leading byte offset [16,30) >> 4 (next core matrix along K) |
+// stride byte offset [32,46) >> 4 (next 8-row group along M/N) | version [46,48) = 1 | layout type [61,64) = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format BF16 = 1 @7/@10,
+// a/b major K = 0 @15/@16, N >> 3 @17, M >> 4 @24
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// counter-based standard normal: threefry2x32 (same block function as the env's jax.random port) + Box-Muller
+__device__ __forceinline__ uint32_t rotl32p(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ void threefry_p(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  const int R[8] = {13, 15, 26, 6, 17, 29, 16, 24};
+  x0 += ks[0]; x1 += ks[1];
+#pragma unroll 1
+  for (int g = 0; g < 5; g++) {
+    for (int i = 0; i < 4; i++) { x0 += x1; x1 = rotl32p(x1, R[(g & 1) * 4 + i]); x1 ^= x0; }
+    x0 += ks[(g + 1) % 3]; x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+  }
+}
+__device__ float normal_draw(uint64_t seed, uint64_t step, uint32_t row, uint32_t j) {
+  uint32_t x0 = row, x1 = j ^ ((uint32_t)step << 8);
+  threefry_p((uint32_t)seed ^ (uint32_t)(step >> 24), (uint32_t)(seed >> 32) + 0x9E3779B9u, x0, x1);
+  const float u1 = ((x0 >> 8) + 1u) * (1.0f / 16777216.0f);   // (0, 1]
+  const float u2 = (x1 >> 8) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POL_TM, 1)
+pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step,
+                   int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
+                   float* __restrict__ log_prob, float* __restrict__ logits_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB[2] = {smem + POL_A_BYTES, smem + POL_A_BYTES + POL_BCHUNK};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + POL_A_BYTES + 2 * POL_BCHUNK);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * POL_TM;
+
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // layer-0 A operand: normalised obs, bf16, canonical K-major layout (LBO = 128 B, SBO = Kp * 16 B)
+  {
+    const PolicyLayer& L0 = P.L[0];
+    const uint32_t sbo = (uint32_t)L0.Kp * 16u;
+    for (int r = warp; r < POL_TM; r += 4) {
+      const int row = row0 + r;
+      for (int k = lane; k < L0.Kp; k += 32) {
+        float v = 0.f;
+        if (row < n_rows && k < L0.K) v = (obs[(size_t)row * P.obs_dim + k] - P.mean[k]) * P.inv_std[k];
+        const uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16_rn(v);
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  int g = 0;   // global chunk counter: chunk g uses buffer g & 1, phase g >> 1 of bars[g & 1]
+  for (int l = 0; l < P.n_layers; l++) {
+    const PolicyLayer& L = P.L[l];
+    const uint32_t a_sbo = (uint32_t)L.Kp * 16u, b_sbo = (uint32_t)L.Kc * 16u;
+    const int chunk_bytes = L.Np * L.Kc * 2;
+    for (int c = 0; c < L.nchunks; c++, g++) {
+      uint8_t* buf = sB[g & 1];
+      if (g >= 2) mbar_wait(&bars[g & 1], (uint32_t)(((g >> 1) - 1) & 1));   // MMAs that read this buffer are done
+      const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(P.w + L.w_off) + (size_t)c * chunk_bytes);
+      int4* dst = reinterpret_cast<int4*>(buf);
+      for (int i = tid; i < chunk_bytes / 16; i += POL_TM) dst[i] = __ldg(src + i);
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const int nslices = L.Kc / 16;
+        for (int s = 0; s < nslices; s++) {
+          const int kslice = c * nslices + s;
+          const uint32_t a_addr = smem_u32(sA) + (uint32_t)kslice * 256u;   // 2 core matrices (16 k) per slice
+          const uint32_t b_addr = smem_u32(buf) + (uint32_t)s * 256u;
+          for (int n0 = 0; n0 < L.Np; n0 += 256) {
+            const int nn = (L.Np - n0) < 256 ? (L.Np - n0) : 256;
+            umma_bf16(tmem + (uint32_t)n0, make_desc(a_addr, 128u, a_sbo), make_desc(b_addr + (uint32_t)(n0 >> 3) * b_sbo, 128u, b_sbo),
+                      make_idesc(POL_TM, nn), (uint32_t)(kslice > 0));
+          }
+        }
+        umma_commit(&bars[g & 1]);
+      }
+    }
+    // whole layer accumulated: wait for the last commit (MMAs retire in issue order)
+    mbar_wait(&bars[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
+    tc_fence_after();
+    const int r = tid, row = row0 + r;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* bias = P.bias + L.b_off;
+    if (l + 1 < P.n_layers) {
+      const uint32_t sbo_next = (uint32_t)P.L[l + 1].Kp * 16u;   // == Np of this layer
+      for (int n0 = 0; n0 < L.Np; n0 += 8) {
+        float v[8];
+        tmem_ld8(trow + (uint32_t)n0, v);
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float a = v[2 * i] + bias[n0 + 2 * i], b = v[2 * i + 1] + bias[n0 + 2 * i + 1];
+          a = (n0 + 2 * i < L.N) ? a / (1.f + __expf(-a)) : 0.f;          // SiLU (swish)
+          b = (n0 + 2 * i + 1 < L.N) ? b / (1.f + __expf(-b)) : 0.f;
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        const uint32_t off = (uint32_t)(r >> 3) * sbo_next + (uint32_t)(n0 >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+        *reinterpret_cast<uint4*>(sA + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    } else {
+      // distribution head: logits = [loc | scale_raw], brax NormalTanhDistribution(min_std = 0.001)
+      float out[32];
+      for (int n0 = 0; n0 < L.Np && n0 < 32; n0 += 8) tmem_ld8(trow + (uint32_t)n0, out + n0);
+      if (row < n_rows) {
+        const int A = P.act_dim;
+        float lp = 0.f;
+        for (int j = 0; j < A; j++) {
+          const float loc = out[j] + bias[j], sr = out[A + j] + bias[A + j];
+          if (logits_out) { logits_out[(size_t)row * 2 * A + j] = loc; logits_out[(size_t)row * 2 * A + A + j] = sr; }
+          const float scale = (sr > 20.f ? sr : log1pf(expf(sr))) + 0.001f;
+          float e = 0.f;
+          if (!deterministic) e = eps_in ? eps_in[(size_t)row * A + j] : normal_draw(seed, step, (uint32_t)row, (uint32_t)j);
+          const float raw = loc + scale * e;
+          // log N(raw; loc, scale) - log|d tanh / d raw|, with log det = 2 (log 2 - raw - softplus(-2 raw))
+          const float m2 = -2.f * raw;
+          const float sp = m2 > 20.f ? m2 : log1pf(expf(m2));
+          lp += -0.5f * e * e - logf(scale) - 0.9189385332046727f - 2.f * (0.6931471805599453f - raw - sp);
+          action[(size_t)row * A + j] = tanhf(raw);
+          if (raw_action) raw_action[(size_t)row * A + j] = raw;
+        }
+        if (log_prob) log_prob[row] = lp;
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// HBM-bound copy of one rollout slot (transition write-out in the learner's [T, N, .] layout)
+__global__ void pgtt_store_slot_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side + C ABI
+// ----------------------------------------------------------------------------------------------
+struct pgtt_policy {
+  int device;
+  PolicyParams P;
+  __nv_bfloat16* w_dev;
+  float *bias_dev, *mean_dev, *istd_dev;
+  size_t w_elems, b_elems;
+  bool has_params;
+  int64_t launches;
+};
+
+static thread_local std::string g_perr;
+static int pfail(int code, const std::string& m) { g_perr = m; return code; }
+#define PCUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return pfail(PGTT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+static uint16_t f2bf(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+extern "C" {
+
+const char* pgtt_policy_last_error(void) { return g_perr.c_str(); }
+
+int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy** out) {
+  if (!sizes || !out || n_layers < 2 || n_layers > POL_MAXLAYERS) return pfail(PGTT_ERR_ARG, "pgtt_policy_create: need 2..6 layers");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(PGTT_ERR_CUDA, "pgtt_policy_create: no CUDA device");
+  if (device < 0 || device >= ndev) return pfail(PGTT_ERR_ARG, "pgtt_policy_create: bad device");
+  pgtt_policy* p = new pgtt_policy();
+  memset(&p->P, 0, sizeof(p->P));
+  p->device = device; p->has_params = false; p->launches = 0;
+  p->w_dev = nullptr; p->bias_dev = p->mean_dev = p->istd_dev = nullptr;
+  PolicyParams& P = p->P;
+  P.n_layers = n_layers; P.obs_dim = sizes[0]; P.act_dim = sizes[n_layers] / 2;
+  size_t w_off = 0, b_off = 0;
+  for (int l = 0; l < n_layers; l++) {
+    PolicyLayer& L = P.L[l];
+    L.K = sizes[l]; L.N = sizes[l + 1];
+    L.Np = (L.N + 15) / 16 * 16;
+    int kc = (POL_BCHUNK / 2 / L.Np) / 16 * 16;
+    const int kp16 = (L.K + 15) / 16 * 16;
+    if (kc > kp16) kc = kp16;
+    if (kc < 16 || L.Np > 512 || (l > 0 && L.K != P.L[l - 1].N)) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: unsupported layer sizes"); }
+    L.Kc = kc;
+    L.Kp = (l == 0) ? (L.K + kc - 1) / kc * kc : P.L[l - 1].Np;   // layer l > 0 reads the padded output of layer l - 1
+    if (L.Kp % kc != 0) { L.Kc = 16; }
+    L.nchunks = L.Kp / L.Kc;
+    if (L.Kp > POL_MAXK) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: layer wider than 512"); }
+    L.w_off = w_off; L.b_off = b_off;
+    w_off += (size_t)L.Np * L.Kp; b_off += L.Np;
+  }
+  if (P.L[n_layers - 1].Np > 32 || sizes[n_layers] % 2) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: head must be 2 * act_dim <= 32"); }
+  p->w_elems = w_off; p->b_elems = b_off;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->w_dev, w_off * 2) != cudaSuccess || cudaMalloc(&p->bias_dev, b_off * 4) != cudaSuccess ||
+      cudaMalloc(&p->mean_dev, P.obs_dim * 4) != cudaSuccess || cudaMalloc(&p->istd_dev, P.obs_dim * 4) != cudaSuccess ||
+      cudaFuncSetAttribute(pgtt_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POL_SMEM) != cudaSuccess) {
+    delete p; return pfail(PGTT_ERR_CUDA, std::string("pgtt_policy_create: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  P.w = p->w_dev; P.bias = p->bias_dev; P.mean = p->mean_dev; P.inv_std = p->istd_dev;
+  *out = p;
+  return PGTT_OK;
+}
+
+int pgtt_policy_destroy(pgtt_policy* p) {
+  if (!p) return PGTT_OK;
+  cudaSetDevice(p->device); cudaDeviceSynchronize();
+  cudaFree(p->w_dev); cudaFree(p->bias_dev); cudaFree(p->mean_dev); cudaFree(p->istd_dev);
+  delete p;
+  return PGTT_OK;
+}
+
+// kernels[l]: HOST fp32 [in][out] row-major (brax / flax `kernel` layout), biases[l]: HOST fp32 [out];
+// obs_mean / obs_std: HOST fp32 [obs_dim] (running-statistics normaliser; NULL = identity)
+int pgtt_policy_set_params(pgtt_policy* p, const float* const* kernels, const float* const* biases, const float* obs_mean, const float* obs_std) {
+  if (!p || !kernels || !biases) return pfail(PGTT_ERR_ARG, "pgtt_policy_set_params: null argument");
+  const PolicyParams& P = p->P;
+  std::vector<uint16_t> w(p->w_elems, 0);
+  std::vector<float> b(p->b_elems, 0.f), mean(P.obs_dim, 0.f), istd(P.obs_dim, 1.f);
+  for (int l = 0; l < P.n_layers; l++) {
+    const PolicyLayer& L = P.L[l];
+    const size_t chunk_elems = (size_t)L.Np * L.Kc;
+    for (int k = 0; k < L.K; k++)
+      for (int n = 0; n < L.N; n++) {
+        const int c = k / L.Kc, kk = k % L.Kc;
+        const size_t off_bytes = (size_t)(n >> 3) * (L.Kc * 16) + (size_t)(kk >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(kk & 7) * 2;
+        w[L.w_off + c * chunk_elems + off_bytes / 2] = f2bf(kernels[l][(size_t)k * L.N + n]);
+      }
+    for (int n = 0; n < L.N; n++) b[L.b_off + n] = biases[l][n];
+  }
+  if (obs_mean) for (int i = 0; i < P.obs_dim; i++) mean[i] = obs_mean[i];
+  if (obs_std) for (int i = 0; i < P.obs_dim; i++) istd[i] = 1.0f / obs_std[i];
+  PCUDA(cudaSetDevice(p->device));
+  PCUDA(cudaDeviceSynchronize());
+  PCUDA(cudaMemcpy(p->w_dev, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+  PCUDA(cudaMemcpy(p->bias_dev, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  PCUDA(cudaMemcpy(p->mean_dev, mean.data(), mean.size() * 4, cudaMemcpyHostToDevice));
+  PCUDA(cudaMemcpy(p->istd_dev, istd.data(), istd.size() * 4, cudaMemcpyHostToDevice));
+  p->has_params = true;
+  return PGTT_OK;
+}
+
+// obs DEVICE [n][obs_dim]; eps DEVICE [n][act_dim] or NULL (internal counter-based normal draws keyed by
+// seed/step); outputs DEVICE: action [n][act_dim], raw_action [n][act_dim] or NULL, log_prob [n] or NULL,
+// logits [n][2 act_dim] or NULL.
+int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint64_t step, int deterministic, const float* eps,
+                    float* action, float* raw_action, float* log_prob, float* logits, void* stream) {
+  if (!p || !obs || !action || n <= 0) return pfail(PGTT_ERR_ARG, "pgtt_policy_act: null argument or n <= 0");
+  if (!p->has_params) return pfail(PGTT_ERR_STATE, "pgtt_policy_act: pgtt_policy_set_params first");
+  const int blocks = (n + POL_TM - 1) / POL_TM;
+  pgtt_policy_kernel<<<blocks, POL_TM, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
+                                                                        deterministic, eps, action, raw_action, log_prob, logits);
+  PCUDA(cudaGetLastError());
+  p->launches++;
+  return PGTT_OK;
+}
+
+// dst[slot] <- src for a [T][n_floats] rollout buffer (both DEVICE)
+int pgtt_store_slot(const float* src, float* dst_base, int slot, size_t n_floats, void* stream) {
+  if (!src || !dst_base) return pfail(PGTT_ERR_ARG, "pgtt_store_slot: null argument");
+  const int threads = 256;
+  const size_t blocks = (n_floats + threads - 1) / threads;
+  pgtt_store_slot_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(src, dst_base + (size_t)slot * n_floats, n_floats);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
+int64_t pgtt_policy_launch_count(pgtt_policy* p) { return p ? p->launches : 0; }
+
+}  // extern "C"

@@ -456,8 +456,32 @@ def extra_vectors(out_dir):
     print("wrote reference_config.json")
 
 
+def policy_vectors(out_dir):
+    """policy177 (one of the two policies policy_folder/README.md:7 calls best): weights + running statistics as
+    loaded by policy_io.load_policy, and the deployment forward `tanh(loc)` computed by the REFERENCE network
+    class deploy/policy_net.py:35-64 (torch) on obs drawn around the normaliser statistics."""
+    import importlib.util
+    import torch
+    from phase_guided_terrain_traversal_b200 import policy_io
+    d = policy_io.load_policy(REF / "policy_folder" / "policy177")
+    spec = importlib.util.spec_from_file_location("ref_policy_net", REF / "deploy" / "policy_net.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    ks, bs = d["policy"]
+    net = ref.MLP(ks, bs, torch.nn.SiLU(), d["mean"], d["std"])
+    g = np.random.default_rng(7)
+    obs = (d["mean"] + d["std"] * g.normal(size=(64, 171)).clip(-3, 3)).astype(np.float32)
+    with torch.no_grad():
+        act = net(torch.from_numpy(obs)).numpy()
+    np.savez_compressed(Path(out_dir) / "policy177.npz", obs=obs, action_deterministic=act.astype(np.float32), mean=d["mean"], std=d["std"],
+                        count=np.float64(d["count"]), **{f"kernel{i}": k for i, k in enumerate(ks)}, **{f"bias{i}": b for i, b in enumerate(bs)},
+                        priv_mean=d["value_mean"], priv_std=d["value_std"])
+    print("wrote policy177.npz")
+
+
 if __name__ == "__main__":
     out_dir = Path(__file__).resolve().parent
+    policy_vectors(out_dir)
     extra_vectors(out_dir)
     run_case("flat", "flat_terrain", None, dr=1, seeds=[0, 1], n_steps=12, out_dir=out_dir)
     run_case("stairs_level07", "stairs", "level07", dr=1, seeds=[0, 1, 2], n_steps=12, out_dir=out_dir)

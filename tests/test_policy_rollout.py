@@ -1,0 +1,114 @@
+"""Policy kernel (tcgen05, bf16 operands / fp32 accumulate) and the rollout collector.
+
+Numerics: against a plain-torch fp32 statement of the same acting step (policy.reference_forward).
+Tolerances: vs the reference with bf16-rounded operands 2e-3 abs on logits (accumulation order only);
+vs pure fp32 5e-2 abs (bf16 operand rounding through four layers)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_policy_pickle_roundtrip(tmp_path):
+    """save_policy / load_policy keep the (RunningStatisticsState, PPONetworkParams) layout deploy/policy_net.py reads."""
+    from phase_guided_terrain_traversal_b200 import policy_io
+    g = np.random.default_rng(0)
+    sizes = [171, 512, 256, 128, 24]
+    ks = [g.normal(size=(i, o)).astype(np.float32) for i, o in zip(sizes[:-1], sizes[1:])]
+    bs = [g.normal(size=o).astype(np.float32) for o in sizes[1:]]
+    mean, std = g.normal(size=171).astype(np.float32), g.uniform(0.5, 2, 171).astype(np.float32)
+    policy_io.save_policy(tmp_path / "p", mean, std, (ks, bs), count=5.0)
+    d = policy_io.load_policy(tmp_path / "p")
+    assert all(np.array_equal(a, b) for a, b in zip(d["policy"][0], ks)) and all(np.array_equal(a, b) for a, b in zip(d["policy"][1], bs))
+    assert np.array_equal(d["mean"], mean) and np.array_equal(d["std"], std) and d["count"] == 5.0
+
+
+def test_reference_forward_matches_reference_network_golden():
+    """The torch fp32 statement used as kernel reference reproduces deploy/policy_net.py on policy177 (fixture)."""
+    from phase_guided_terrain_traversal_b200.policy import reference_forward
+    g = np.load(GOLD / "policy177.npz")
+    ks, bs = [g[f"kernel{i}"] for i in range(4)], [g[f"bias{i}"] for i in range(4)]
+    out = reference_forward(ks, bs, g["obs"], g["mean"], g["std"])
+    assert np.abs(out["action"].numpy() - g["action_deterministic"]).max() < 2e-5
+    # the shipped normaliser statistics carry the distributional pins of SURVEY 8c-3
+    assert abs(g["mean"][5] + 0.991) < 5e-3 and np.allclose(g["std"][30:38], 0.7075, atol=2e-3) and abs(g["mean"][155] - 2.01) < 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 100, 128, 4096])
+def test_policy_kernel_vs_torch_reference(n):
+    import torch
+    from phase_guided_terrain_traversal_b200.policy import PolicyNet, reference_forward
+    g = np.load(GOLD / "policy177.npz")
+    ks, bs = [g[f"kernel{i}"] for i in range(4)], [g[f"bias{i}"] for i in range(4)]
+    net = PolicyNet()
+    net.set_params(ks, bs, g["mean"], g["std"])
+    rng = np.random.default_rng(n)
+    obs = (g["mean"] + g["std"] * rng.normal(size=(n, 171)).clip(-3, 3)).astype(np.float32)
+    eps = rng.normal(size=(n, 12)).astype(np.float32)
+    out = net.act(torch.from_numpy(obs).cuda(), eps=torch.from_numpy(eps).cuda(), want_logits=True)
+    torch.cuda.synchronize()
+    ref_bf = reference_forward(ks, bs, obs, g["mean"], g["std"], eps, bf16_operands=True)
+    ref_32 = reference_forward(ks, bs, obs, g["mean"], g["std"], eps)
+    lg = out["logits"].cpu()
+    assert (lg - ref_bf["logits"]).abs().max() < 2e-3, (lg - ref_bf["logits"]).abs().max()
+    assert (lg - ref_32["logits"]).abs().max() < 5e-2
+    assert (out["action"].cpu() - ref_bf["action"]).abs().max() < 2e-3
+    assert (out["raw_action"].cpu() - ref_bf["raw_action"]).abs().max() < 5e-3
+    assert ((out["log_prob"].cpu() - ref_bf["log_prob"]).abs() / (1 + ref_bf["log_prob"].abs())).max() < 5e-3
+    det = net.act(torch.from_numpy(obs).cuda(), deterministic=True)
+    assert (det["action"].cpu() - torch.tanh(ref_bf["logits"][:, :12])).abs().max() < 2e-3
+    if n == 4096:   # deployment forward of the reference network on its own fixture obs
+        o2 = net.act(torch.from_numpy(g["obs"]).cuda(), deterministic=True)
+        assert np.abs(o2["action"].cpu().numpy() - g["action_deterministic"]).max() < 3e-2
+
+
+@pytest.mark.gpu
+def test_policy_internal_noise_is_standard_normal():
+    import torch
+    from phase_guided_terrain_traversal_b200.policy import PolicyNet
+    net = PolicyNet().init_random(1)
+    obs = torch.zeros((8192, 171), device="cuda")
+    o = net.act(obs, seed=3, want_logits=True)
+    loc, sr = o["logits"][:, :12], o["logits"][:, 12:]
+    e = (o["raw_action"] - loc) / (torch.nn.functional.softplus(sr) + 0.001)
+    assert abs(float(e.mean())) < 0.02 and abs(float(e.std()) - 1) < 0.02
+    o2 = net.act(obs, seed=3)
+    assert not torch.equal(o2["raw_action"], o["raw_action"])      # the step counter advances the stream
+
+
+@pytest.mark.gpu
+def test_rollout_collector_shapes_and_consistency(train_cfg):
+    """20-step unroll on stairs/level07 driven by policy177: buffers are time-major, next_obs[t] == obs[t + 1],
+    stored actions are what the env consumed (info.last_act), discount = 1 - done, and a trained policy keeps most
+    robots upright (closed loop through physics, obs and policy)."""
+    import functools
+    import torch
+    from phase_guided_terrain_traversal_b200 import prng, terrain
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    from phase_guided_terrain_traversal_b200.go2.randomize import domain_randomize
+    from phase_guided_terrain_traversal_b200.policy import PolicyNet
+    from phase_guided_terrain_traversal_b200.rollout import RolloutCollector
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+    g = np.load(GOLD / "policy177.npz")
+    n, T = 512, 20
+    keys = prng.env_keys(5, n)
+    env = Joystick(task="stairs", config=train_cfg)
+    wenv = wrap_for_brax_training(env, episode_length=1000, randomization_fn=functools.partial(domain_randomize, rng=keys, terrain_matrix=terrain.load_terrain("level07")))
+    state = wenv.reset(keys + np.uint32(9))
+    net = PolicyNet()
+    net.set_params([g[f"kernel{i}"] for i in range(4)], [g[f"bias{i}"] for i in range(4)], g["mean"], g["std"])
+    col = RolloutCollector(wenv, net, unroll_length=T, seed=1)
+    fallen = 0.0
+    for it in range(5):
+        state, ro = col.collect(state)
+        torch.cuda.synchronize()
+        assert ro.obs_state.shape == (T + 1, n, 171) and ro.action.shape == (T, n, 12) and ro.reward.shape == (T, n)
+        assert torch.equal(ro.next_observation["state"][:-1], ro.observation["state"][1:])
+        assert torch.equal(ro.obs_state[-1], state.obs["state"]) and torch.equal(ro.action[-1], state.info["last_act"])
+        assert torch.all((ro.discount == 0) | (ro.discount == 1)) and torch.isfinite(ro.log_prob).all() and (ro.action.abs() <= 1).all()
+        fallen += float((1 - ro.discount).sum()) / n
+    assert fallen < 0.25, fallen                                   # random actions lose ~all robots within 100 steps
+    assert float(ro.reward.mean()) > 0.005
