@@ -17,6 +17,7 @@
 
 #include "pgtt_debug.h"
 #include "pgtt_env.cuh"
+#include "pgtt_quad.cuh"
 
 #define MAX_WARPS_PER_BLOCK 16
 #define WS_BYTES ((sizeof(WS) + 15) / 16 * 16)
@@ -153,6 +154,20 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 1) pgtt_env_kernel(L
   else env_debug_forward(w, a.B, a.out, env, lane);
 }
 
+// generation-2 kernels: one warp per CTA, eight envs per warp (pgtt_quad.cuh). No CTA-level cooperation, so the
+// grid is simply ceil(N / 8) single-warp CTAs: 4096 envs -> 512 warps over the 592 warp schedulers of 148 SMs.
+#define QWARPS_MAX 8
+template <int OP>
+__global__ void __launch_bounds__(32 * QWARPS_MAX) pgtt_quad_kernel(LaunchArgs a) {
+  extern __shared__ float4 smem4[];
+  const int lane = threadIdx.x & 31, warp = warp_index();
+  QShared& sh = *reinterpret_cast<QShared*>(reinterpret_cast<char*>(smem4) + (size_t)warp * ((sizeof(QShared) + 15) / 16 * 16));
+  q_stage_consts(sh, lane);
+  const int env = (blockIdx.x * (blockDim.x >> 5) + warp) * QENV + (lane >> 2);
+  if (OP == OP_STEP) q_env_step(sh, a.B, a.action, env, lane, a.wrapped);
+  else q_env_debug_forward(sh, a.B, a.out, env, lane);
+}
+
 __global__ void pgtt_randomize_kernel(EnvBuffers B, const uint32_t* keys, int dyn) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env < B.N) env_randomize(B, keys, env, dyn);
@@ -165,10 +180,19 @@ static void warp_entry(void* p, int lane) {
   WarpJob* j = (WarpJob*)p;
   dispatch(*j->w, *j->a, j->env, lane);
 }
+struct QuadJob { const LaunchArgs* a; int env0; QShared* sh; };
+static void quad_entry(void* p, int lane) {
+  QuadJob* j = (QuadJob*)p;
+  q_stage_consts(*j->sh, lane);
+  const int env = j->env0 + (lane >> 2);
+  if (j->a->op == OP_STEP) q_env_step(*j->sh, j->a->B, j->a->action, env, lane, j->a->wrapped);
+  else q_env_debug_forward(*j->sh, j->a->B, j->a->out, env, lane);
+}
 #endif
 
 struct pgtt_env {
   int device, N, wpb;
+  int quad;   // 1: generation-2 quad-per-env kernels for step / debug-forward (default), 0: warp-per-env (PGTT_KERNEL=warp)
   ModelConst mc;
   EnvBuffers B;
   std::vector<void*> allocs;
@@ -209,6 +233,17 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
   a.B = e->B;
 #ifndef PGTT_HOST_EMU
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
+    int qw = e->N >= 8192 ? QWARPS_MAX : 1;   // lockstep CTAs once there is more than one warp per scheduler
+    if (const char* s = getenv("PGTT_QUAD_WARPS")) { const int v = atoi(s); if (v >= 1 && v <= QWARPS_MAX) qw = v; }
+    const int qwarps = (e->N + QENV - 1) / QENV, qblocks = (qwarps + qw - 1) / qw;
+    const size_t qsmem = qw * ((sizeof(QShared) + 15) / 16 * 16);
+    if (a.op == OP_STEP) pgtt_quad_kernel<OP_STEP><<<qblocks, 32 * qw, qsmem, st>>>(a);
+    else pgtt_quad_kernel<OP_DEBUG><<<qblocks, 32 * qw, qsmem, st>>>(a);
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+    return 0;
+  }
   const int wpb = e->wpb;
   const int blocks = (e->N + wpb - 1) / wpb;
   const size_t smem = wpb * WS_BYTES;
@@ -222,6 +257,22 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
   CUDA_OK(cudaGetLastError());
 #else
   (void)stream;
+  if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
+    const int nwarps = (e->N + QENV - 1) / QENV;
+#pragma omp parallel
+    {
+      QShared* sh = (QShared*)aligned_alloc(16, (sizeof(QShared) + 15) / 16 * 16);
+#pragma omp for schedule(dynamic, 1)
+      for (int wi = 0; wi < nwarps; wi++) {
+        memset(sh, 0xCD, sizeof(QShared));
+        QuadJob j = {&a, wi * QENV, sh};
+        emu_run_warp(quad_entry, &j);
+      }
+      free(sh);
+    }
+    e->launches++;
+    return 0;
+  }
 #pragma omp parallel
   {
     WS* w = (WS*)aligned_alloc(16, WS_BYTES);
@@ -272,10 +323,18 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t qsmem = QWARPS_MAX * ((sizeof(QShared) + 15) / 16 * 16);
+    CUDA_OK(cudaFuncSetAttribute(pgtt_quad_kernel<OP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
+    CUDA_OK(cudaFuncSetAttribute(pgtt_quad_kernel<OP_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
   }
 #endif
   pgtt_env* e = new pgtt_env();
   e->device = device; e->N = num_envs; e->wpb = pick_warps_per_block(num_envs); e->terrain_dev = nullptr; e->n_terrains = 0; e->launches = 0; e->randomized = false;
+  // Kernel generation for step / debug-forward. Measured on B200 (profiles/r01c): with <= 8192 envs per GPU the
+  // warp-per-env kernel is faster (the quad kernel has one latency-bound warp per scheduler there); from ~12k envs
+  // per GPU the quad kernel in 8-warp lockstep CTAs wins. PGTT_KERNEL=warp|quad overrides.
+  e->quad = num_envs >= 12288;
+  if (const char* k = getenv("PGTT_KERNEL")) e->quad = strcmp(k, "quad") == 0;
   ModelConst& c = e->mc;
   memset(&c, 0, sizeof(c));
   c.dt = (float)m->timestep; c.gravity_z = (float)m->gravity[2]; c.impratio = (float)m->impratio;

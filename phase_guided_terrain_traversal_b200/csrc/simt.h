@@ -30,8 +30,12 @@ DEV void syncwarp() { __syncwarp(); }
 // correctness beyond the warp-level ordering it implies; it keeps the warps of a CTA streaming
 // through the same stretch of code so instruction-cache lines are fetched once per CTA, not once per warp.
 DEV void cta_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+// CTA-wide votes that double as lockstep barriers (quad kernels: every warp of the CTA iterates the same number of times)
+DEV bool cta_any(bool p) { return __syncthreads_or(p) != 0; }
+DEV bool cta_all(bool p) { return __syncthreads_and(p) != 0; }
 DEV int warp_index() { return __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0); }
 DEV float ldg(const float* p) { return __ldg(p); }
+DEV float4 ldg4(const float4* p) { return __ldg(p); }
 DEV int popc(unsigned x) { return __popc(x); }
 DEV int ffs_(unsigned x) { return __ffs((int)x); }
 DEV float rsqrt_(float x) { return rsqrtf(x); }

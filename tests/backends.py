@@ -1,14 +1,23 @@
-"""Back-ends the kernel-parity tests run on: the host-emulated kernel source (CPU, always) and
-the real CUDA library (marked gpu)."""
+"""Back-ends the kernel-parity tests run on: the host-emulated kernel source (CPU, always) and the real CUDA
+library (marked gpu), each with both kernel generations (warp-per-env, quad-per-env; PGTT_KERNEL is read by
+pgtt_create)."""
+import os
+
 import pytest
 
 
 def make_env(kind, model, cfg, n, **kw):
-    if kind == "emu":
-        import emu_backend
-        return emu_backend.make_env(model, cfg, n, **kw)
-    from phase_guided_terrain_traversal_b200.abi_env import AbiEnv
-    return AbiEnv(model, cfg, n, backend="torch", **kw)
+    base, _, gen = kind.partition("-")
+    os.environ["PGTT_KERNEL"] = gen or "warp"
+    try:
+        if base == "emu":
+            import emu_backend
+            return emu_backend.make_env(model, cfg, n, **kw)
+        from phase_guided_terrain_traversal_b200.abi_env import AbiEnv
+        return AbiEnv(model, cfg, n, backend="torch", **kw)
+    finally:
+        os.environ.pop("PGTT_KERNEL", None)
 
 
-BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("emu-quad", id="emu-quad"),
+            pytest.param("cuda", id="cuda", marks=pytest.mark.gpu), pytest.param("cuda-quad", id="cuda-quad", marks=pytest.mark.gpu)]

@@ -77,7 +77,10 @@ DEV bool any_lane(bool p) { return wballot(p) != 0; }
 DEV bool all_lanes(bool p) { return wballot(p) == FULL_MASK; }
 DEV void syncwarp() { emu_barrier(); }
 DEV void cta_bar(int) { emu_barrier(); }
+DEV bool cta_any(bool p) { return any_lane(p); }   // the emulated CTA is one warp
+DEV bool cta_all(bool p) { return all_lanes(p); }
 DEV float ldg(const float* p) { return *p; }
+DEV float4 ldg4(const float4* p) { return *p; }
 DEV int popc(unsigned x) { return __builtin_popcount(x); }
 DEV int ffs_(unsigned x) { return __builtin_ffs((int)x); }
 DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }

@@ -163,7 +163,7 @@ def test_heightscan_matches_oracle_and_numpy(kind, train_cfg):
     center = np.concatenate([rng.uniform(-3.5, 3.5, (N, 2)), rng.uniform(0.2, 0.8, (N, 1))], 1)
     yaw = rng.uniform(-np.pi, np.pi, N)
     ho = orc.scan(center, yaw)
-    hk = np.asarray(env.heightscan(center.astype(np.float32), yaw.astype(np.float32)).cpu() if kind == "cuda" else env.heightscan(center.astype(np.float32), yaw.astype(np.float32)))
+    hk = np.asarray(env.heightscan(center.astype(np.float32), yaw.astype(np.float32)).cpu() if kind.startswith("cuda") else env.heightscan(center.astype(np.float32), yaw.astype(np.float32)))
     assert np.abs(ho[..., :2] - hk[..., :2]).max() < 1e-5
     dz = np.abs(ho[..., 2] - hk[..., 2])
     assert (dz < 1e-5).mean() > 0.995     # a ray within 1 ulp of a box edge may land on either side
