@@ -1,10 +1,10 @@
 """Policy kernel (tcgen05, bf16 operands / fp32 accumulate) and the rollout collector.
 
 Numerics: against a plain-torch fp32 statement of the same acting step (policy.reference_forward).
-Tolerances: vs the reference with bf16-rounded operands 5e-3 abs on logits - typical error is 1e-6
-(accumulation order only), but a hidden activation that lands on a bf16 rounding boundary may round the other
-way (1 bf16 ulp = 2^-8 relative, times a last-layer weight: 2.2e-3 observed on B200); vs pure fp32 5e-2 abs
-(bf16 operand rounding through four layers)."""
+Tolerances: vs the reference with bf16-rounded operands 1e-2 abs on logits with median < 1e-5 and 99 % < 1e-3 -
+the typical error is 1e-7 (accumulation order only), but a hidden activation that lands on a bf16 rounding
+boundary may round the other way (1 bf16 ulp = 2^-8 relative, times downstream weights: up to 5.7e-3 observed
+on B200 in 1 % of rows); vs pure fp32 2 % of the logit scale (bf16 operand rounding through four layers)."""
 from pathlib import Path
 
 import numpy as np
@@ -55,14 +55,21 @@ def test_policy_kernel_vs_torch_reference(n):
     ref_bf = reference_forward(ks, bs, obs, g["mean"], g["std"], eps, bf16_operands=True)
     ref_32 = reference_forward(ks, bs, obs, g["mean"], g["std"], eps)
     lg = out["logits"].cpu()
-    assert (lg - ref_bf["logits"]).abs().max() < 5e-3, (lg - ref_bf["logits"]).abs().max()
-    assert (lg - ref_bf["logits"]).abs().median() < 1e-5
-    assert (lg - ref_32["logits"]).abs().max() < 5e-2
-    assert (out["action"].cpu() - ref_bf["action"]).abs().max() < 2e-2 and (out["action"].cpu() - ref_bf["action"]).abs().median() < 1e-5   # a flipped logit is scaled by |eps| <= 4
-    assert (out["raw_action"].cpu() - ref_bf["raw_action"]).abs().max() < 2e-2
+    # measured on B200 (tools/policy_error_probe.py, n = 4096): median 5e-8, 99 % < 3.4e-4, max 5.7e-3 (45 rows with a
+    # flipped bf16 rounding of a hidden activation); bf16-operand reference vs pure fp32: max 5.7e-2 at |logit| <= 7.2
+    err = (lg - ref_bf["logits"]).abs()
+    assert err.max() < 1e-2, err.max()
+    assert err.median() < 1e-5 and torch.quantile(err.flatten(), 0.99) < 1e-3
+    assert (lg - ref_32["logits"]).abs().max() < 2e-2 * max(1.0, float(ref_32["logits"].abs().max()))
+    # sampling is 1-Lipschitz in the logits (tanh, softplus): |d raw| <= |d loc| + |d scale-logit| * |eps|, |d action| <= |d raw|
+    dl = (lg - ref_bf["logits"]).abs()
+    bound = dl[:, :12] + dl[:, 12:] * torch.from_numpy(eps).abs() + 1e-5
+    assert ((out["raw_action"].cpu() - ref_bf["raw_action"]).abs() <= bound).all()
+    assert ((out["action"].cpu() - ref_bf["action"]).abs() <= bound).all()
+    assert (out["action"].cpu() - ref_bf["action"]).abs().median() < 1e-5
     assert ((out["log_prob"].cpu() - ref_bf["log_prob"]).abs() / (1 + ref_bf["log_prob"].abs())).max() < 2e-2
     det = net.act(torch.from_numpy(obs).cuda(), deterministic=True)
-    assert (det["action"].cpu() - torch.tanh(ref_bf["logits"][:, :12])).abs().max() < 5e-3
+    assert (det["action"].cpu() - torch.tanh(ref_bf["logits"][:, :12])).abs().max() < 1e-2
     if n == 4096:   # deployment forward of the reference network on its own fixture obs
         o2 = net.act(torch.from_numpy(g["obs"]).cuda(), deterministic=True)
         assert np.abs(o2["action"].cpu().numpy() - g["action_deterministic"]).max() < 3e-2
