@@ -123,6 +123,8 @@ class ClockSampler:
 # CPU legs (oracle): the ONLY place bench.py touches oracle/
 # ------------------------------------------------------------------------------------------------
 def make_oracle(args, n, cfg, table, seed_offset=0):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use every host thread
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle.oracle import Oracle
     from phase_guided_terrain_traversal_b200 import model as gm, prng
     m = gm.compile_model(args.task, sim_dt=cfg.sim_dt, Kp=cfg.Kp, Kd=cfg.Kd)
@@ -299,6 +301,26 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     sampler.stop()
 
+    # ---- region D: the PPO rollout collector: policy MLP (tcgen05) -> env step -> transition record,
+    # unroll_length 20, everything on the device, one native call per unroll ------------------------------------------------
+    from phase_guided_terrain_traversal_b200.policy import PolicyNet
+    from phase_guided_terrain_traversal_b200.rollout import RolloutCollector
+    T = 20
+    net = PolicyNet(device=local_rank).init_random(1 + rank)
+    col = RolloutCollector(wenv, net, unroll_length=T, seed=7 + rank)
+    n_unroll = max(2, K // T)
+    for _ in range(2):
+        col.collect()
+    barrier()
+    l0r = abi.launch_count() + net.launch_count()
+    e0.record(stream)
+    for _ in range(n_unroll):
+        col.collect()
+    e1.record(stream)
+    barrier()
+    ms_rollout = max_over_ranks(e0.elapsed_time(e1))
+    rollout_launches = abi.launch_count() + net.launch_count() - l0r
+
     done_rate = float(state.done.float().mean().item())
     niter = float(abi.buf["solver_niter"].float().mean().item())
     finite = bool(torch.isfinite(state.data.qpos).all().item())
@@ -316,6 +338,10 @@ def main():
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * 12 * 4, "d2h_bytes_per_step": N * 2 * 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
+            "rollout": {"value": total_envs * T * n_unroll / (ms_rollout * 1e-3), "unit": UNIT, "unroll_length": T, "unrolls": n_unroll,
+                        "ms_per_env_step_batch": ms_rollout / (T * n_unroll), "gpu_launches": int(rollout_launches),
+                        "what": "policy MLP 171-512-256-128-24 (tcgen05, bf16 operands, fp32 accumulate, random init) + wrapped env step + "
+                                "transition record into [T,N,.] buffers; back-to-back (no L2 flush)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "kernel": "pgtt_env_kernel<OP_STEP>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_env_step": B_ALG,

@@ -12,7 +12,7 @@
  *   pgtt_step              wrapped env.step                          go2/joystick_pgtt.py:141-231, training/train.py:255
  *   pgtt_heightscan        create_sensor_matrix                      go2/heightmap.py:25-67
  *   pgtt_forward           mjx.forward on the current state          go2/joystick_pgtt.py:78
- *   pgtt_policy_step /     brax ppo acting step + generate_unroll    training/train.py:135-161,242-263
+ *   pgtt_policy_act /      brax ppo acting step + generate_unroll    training/train.py:135-161,242-263
  *   pgtt_rollout
  *   pgtt_get_buffers       State / info / data field access          go2/joystick_pgtt.py:101-131
  *
@@ -169,6 +169,23 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
 /* transition write-out: dst_base[slot][0..n_floats) <- src[0..n_floats) (both DEVICE) */
 int pgtt_store_slot(const float* src, float* dst_base, int slot, size_t n_floats, void* stream);
 int64_t pgtt_policy_launch_count(pgtt_policy* p);
+
+/* One launch that files the current step's results into a time-major rollout slot: obs_state_dst / obs_priv_dst
+ * <- obs (next_observation), reward_dst <- reward, discount_dst <- 1 - done, truncation_dst <- truncation.
+ * All DEVICE pointers to ONE slot ([num_envs][dim]); any may be NULL. */
+int pgtt_record(pgtt_env* env, float* obs_state_dst, float* obs_priv_dst, float* reward_dst, float* discount_dst, float* truncation_dst,
+                void* stream);
+
+/* brax generate_unroll (training/train.py:135-161,242-263): T x (policy act -> wrapped env step -> record), all
+ * launches issued natively on `stream` (3 kernels per control step, nothing returns to the host in between).
+ * Buffers are DEVICE, time-major: obs_* [T + 1][N][dim] (slot 0 = the observation the unroll starts from, so
+ * next_observation[t] = observation[t + 1]); action / raw_action [T][N][12]; log_prob / reward / discount /
+ * truncation [T][N]. Internal exploration noise is keyed by (seed, step0 + t). */
+typedef struct {
+  float *obs_state, *obs_privileged, *action, *raw_action, *log_prob, *reward, *discount, *truncation;
+} pgtt_rollout_buffers;
+int pgtt_rollout(pgtt_env* env, pgtt_policy* policy, int T, uint64_t seed, uint64_t step0, int deterministic,
+                 const pgtt_rollout_buffers* out, void* stream);
 
 #ifdef __cplusplus
 }

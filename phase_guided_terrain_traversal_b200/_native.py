@@ -99,6 +99,10 @@ class Buffers(C.Structure):
     _fields_ = [("num_envs", i32)] + [(n, C.POINTER(_CT[k])) for n, k, _ in BUFFER_FIELDS]
 
 
+class RolloutBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs_state", "obs_privileged", "action", "raw_action", "log_prob", "reward", "discount", "truncation")]
+
+
 REWARD_KEYS = [
     "tracking_lin_vel", "tracking_ang_vel", "lin_vel_z", "ang_vel_xy", "orientation", "dof_pos_limits", "pose",
     "termination", "stand_still", "torques", "action_rate", "energy", "feet_clearance", "feet_height", "feet_slip",
@@ -185,6 +189,7 @@ def declare(lib):
     lib.pgtt_debug_forward.argtypes = [vp, vp, vp]
     lib.pgtt_launch_count.argtypes = [vp]
     lib.pgtt_launch_count.restype = C.c_int64
+    lib.pgtt_record.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     if hasattr(lib, "pgtt_policy_create"):     # absent from the host-emulated test library (env kernels only)
         lib.pgtt_policy_last_error.restype = C.c_char_p
         lib.pgtt_policy_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
@@ -194,14 +199,15 @@ def declare(lib):
         lib.pgtt_store_slot.argtypes = [vp, vp, C.c_int, C.c_size_t, vp]
         lib.pgtt_policy_launch_count.argtypes = [vp]
         lib.pgtt_policy_launch_count.restype = C.c_int64
+        lib.pgtt_rollout.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(RolloutBuffers), vp]
     return lib
 
 
 ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
-    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_debug_forward", "pgtt_launch_count",
+    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act", "pgtt_store_slot",
-    "pgtt_policy_launch_count",
+    "pgtt_policy_launch_count", "pgtt_rollout",
 ]
 
 _LIB = None

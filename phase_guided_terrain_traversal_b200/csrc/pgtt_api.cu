@@ -168,6 +168,21 @@ __global__ void __launch_bounds__(32 * QWARPS_MAX) pgtt_quad_kernel(LaunchArgs a
   else q_env_debug_forward(sh, a.B, a.out, env, lane);
 }
 
+// transition write-out: one HBM-bound launch per control step (obs 171 + 215 floats, 3 scalars per env)
+__global__ void pgtt_record_kernel(EnvBuffers B, float* __restrict__ os, float* __restrict__ op, float* __restrict__ rw, float* __restrict__ dc,
+                                   float* __restrict__ tr) {
+  const size_t n_os = (size_t)B.N * NOBS, n_op = (size_t)B.N * NPRIV, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_op; i += stride) {
+    if (op) op[i] = B.obs_priv[i];
+    if (os && i < n_os) os[i] = B.obs_state[i];
+    if (i < (size_t)B.N) {
+      if (rw) rw[i] = B.reward[i];
+      if (dc) dc[i] = 1.0f - B.done[i];
+      if (tr) tr[i] = B.truncation[i];
+    }
+  }
+}
+
 __global__ void pgtt_randomize_kernel(EnvBuffers B, const uint32_t* keys, int dyn) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env < B.N) env_randomize(B, keys, env, dyn);
@@ -584,5 +599,30 @@ int pgtt_get_buffers(pgtt_env* e, pgtt_buffers* o) {
 }
 
 int64_t pgtt_launch_count(pgtt_env* e) { return e ? e->launches : 0; }
+
+int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* tr, void* stream) {
+  if (!e) return fail(PGTT_ERR_ARG, "pgtt_record: null handle");
+  const EnvBuffers& B = e->B;
+#ifndef PGTT_HOST_EMU
+  const size_t n = (size_t)B.N * NPRIV;
+  const int threads = 256;
+  size_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pgtt_record_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(B, os, op, rw, dc, tr);
+  CUDA_OK(cudaGetLastError());
+#else
+  (void)stream;
+  const size_t N = (size_t)B.N;
+  if (os) memcpy(os, B.obs_state, N * NOBS * sizeof(float));
+  if (op) memcpy(op, B.obs_priv, N * NPRIV * sizeof(float));
+  for (size_t i = 0; i < N; i++) {
+    if (rw) rw[i] = B.reward[i];
+    if (dc) dc[i] = 1.0f - B.done[i];
+    if (tr) tr[i] = B.truncation[i];
+  }
+#endif
+  e->launches++;
+  return PGTT_OK;
+}
 
 }  // extern "C"

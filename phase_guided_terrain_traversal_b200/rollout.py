@@ -5,7 +5,8 @@ fused env step kernel -> transition write-out. Transitions are stored time-major
 layout the learner consumes (brax `Transition(observation, action, reward, discount, next_observation,
 extras{policy_extras{log_prob, raw_action}, state_extras{truncation}})`); observations are kept as
 `[T + 1, N, ...]` so `next_observation[t] = observation[t + 1]` (what the auto-reset wrapper returns).
-Everything stays on the device; the three kernels per step are launched on the caller's stream.
+Everything stays on the device: `collect` is ONE native call (`pgtt_rollout`) that issues the three kernels
+per control step (policy, env step, transition record) on the caller's stream.
 """
 from __future__ import annotations
 
@@ -50,30 +51,22 @@ class RolloutCollector:
         N, T, dev = abi.N, self.T, abi.torch_device
         f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         self.buf = Rollout(f(T + 1, N, 171), f(T + 1, N, 215), f(T, N, 12), f(T, N, 12), f(T, N), f(T, N), f(T, N), f(T, N))
-        self._act_out = [{"action": self.buf.action[t], "raw_action": self.buf.raw_action[t], "log_prob": self.buf.log_prob[t]} for t in range(T)]
+        self._step = 0      # exploration-noise counter: advances by T per collect
 
-    def _store(self, src, dst, slot):
-        n = src.numel()
+    def collect(self, state=None, deterministic: bool = False) -> tuple:
+        """Runs `unroll_length` control steps from the env's current state; returns (final state, Rollout).
+        One native call (`pgtt_rollout`): 1 + 3 T kernel launches on the current stream, nothing returns to the host."""
+        buf = self.buf
+        if state is not None and not (state._live and state._owner is self.env):
+            self.env.set_state(state)
+        rb = nat.RolloutBuffers(*(C.c_void_p(t.data_ptr()) for t in (buf.obs_state, buf.obs_privileged, buf.action, buf.raw_action, buf.log_prob,
+                                                                     buf.reward, buf.discount, buf.truncation)))
         stream = C.c_void_p(self.torch.cuda.current_stream(self.abi.torch_device).cuda_stream)
-        rc = self.lib.pgtt_store_slot(src.data_ptr(), dst.data_ptr(), slot, n, stream)
+        rc = self.lib.pgtt_rollout(self.abi.h, self.policy.h, self.T, C.c_uint64(self.seed), C.c_uint64(self._step), int(deterministic), C.byref(rb), stream)
         if rc:
-            raise nat.PgttError(rc, self.lib.pgtt_policy_last_error().decode())
-
-    def collect(self, state, deterministic: bool = False) -> tuple:
-        """Runs `unroll_length` control steps from `state`; returns (final state, Rollout)."""
-        b, buf = self.abi.buf, self.buf
-        self._store(b["obs_state"], buf.obs_state, 0)
-        self._store(b["obs_privileged"], buf.obs_privileged, 0)
-        for t in range(self.T):
-            self.policy.act(buf.obs_state[t], seed=self.seed, deterministic=deterministic, out=self._act_out[t])
-            self.abi.step_ptr(buf.action[t].data_ptr(), wrapped=True)
-            self._store(b["obs_state"], buf.obs_state, t + 1)
-            self._store(b["obs_privileged"], buf.obs_privileged, t + 1)
-            self._store(b["reward"], buf.reward, t)
-            self._store(b["done"], buf.discount, t)
-            self._store(b["truncation"], buf.truncation, t)
-        buf.discount.neg_().add_(1.0)        # discount = 1 - done
+            raise nat.PgttError(rc, (self.lib.pgtt_policy_last_error() or self.lib.pgtt_last_error()).decode())
+        self._step += self.T
         return self.env._live_state(), buf
 
     def launches_per_collect(self) -> int:
-        return 2 + self.T * 7
+        return 1 + self.T * 3
