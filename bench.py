@@ -129,6 +129,11 @@ def make_oracle(args, n, cfg, table, seed_offset=0):
     from phase_guided_terrain_traversal_b200 import model as gm, prng
     m = gm.compile_model(args.task, sim_dt=cfg.sim_dt, Kp=cfg.Kp, Kd=cfg.Kd)
     orc = Oracle(m, cfg, n, "f32native")   # gcc -O3 -march=native, built on this host
+    try:                                   # libgomp may have read OMP_NUM_THREADS=1 before the line above changed it
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count() or 1)
+    except OSError:
+        pass
     keys = prng.env_keys(0, n, seed_offset)
     orc.randomize(keys, table if args.task == "stairs" else None, bool(args.dr))
     orc.reset(keys + np.uint32(1))

@@ -5,13 +5,14 @@
 // (same network re-hosted in torch): normalise obs -> 171->512->256->128->24 MLP -> loc | scale ->
 // raw = loc + (softplus(scale) + 0.001) * eps -> action = tanh(raw), log_prob.
 //
-// One CTA (128 threads) owns a tile of 128 envs and runs the WHOLE network for it in one launch:
+// One CTA (256 threads) owns a tile of 128 envs and runs the WHOLE network for it in one launch:
 //   * activations live in shared memory as the K-major A operand (bf16, canonical no-swizzle UMMA layout),
-//   * weights are pre-packed on the host into the same canonical layout (B operand, K-chunks of <= 32 KB,
-//     double-buffered in shared memory),
+//   * weights are pre-packed on the host into the same canonical layout (B operand, K-chunks of <= 32 KB) and
+//     stream through a double buffer with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that run one
+//     chunk ahead of the MMAs,
 //   * `tcgen05.mma.cta_group::1.kind::f16` (M = 128, N <= 256, K = 16 per instruction) issued by one
 //     thread accumulates a whole layer in TMEM (fp32, up to 512 columns),
-//   * after `tcgen05.commit` -> mbarrier, the four warps read their 32 TMEM lanes with `tcgen05.ld`,
+//   * after `tcgen05.commit` -> mbarrier, the eight warps read their TMEM lane quarter / column half with `tcgen05.ld` x32,
 //     apply bias + SiLU and write the next layer's A operand in place; the last layer's epilogue does
 //     the distribution math and writes action / raw_action / log_prob.
 // bf16 operands, fp32 accumulation (north-star: "policy MLP on tensor cores, bf16 in, fp32 accumulate").
@@ -30,9 +31,11 @@
 #define POL_TM 128            // envs per CTA = MMA M
 #define POL_MAXK 512          // widest activation
 #define POL_MAXLAYERS 6
-#define POL_BCHUNK 32768      // bytes per weight chunk buffer
+#define POL_BCHUNK 16384      // bytes per weight chunk buffer
+#define POL_NBUF 5            // chunk buffers: up to 4 TMA bulk copies in flight ahead of the MMAs
+#define POL_MAXBIAS 1024      // padded biases of all layers, staged in shared memory
 #define POL_A_BYTES (POL_TM * POL_MAXK * 2)
-#define POL_SMEM (POL_A_BYTES + 2 * POL_BCHUNK + 64)
+#define POL_SMEM (POL_A_BYTES + POL_NBUF * POL_BCHUNK + POL_MAXBIAS * 4 + 128)   // + 2 NBUF + 1 mbarriers and the TMEM slot
 
 struct PolicyLayer {
   int K, N, Kp, Np, Kc, nchunks;   // true sizes, padded sizes, K per chunk
@@ -128,34 +131,114 @@ __device__ float normal_draw(uint64_t seed, uint64_t step, uint32_t row, uint32_
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(POL_TM, 1)
+#define POL_EPI_THREADS 256   // 8 epilogue warps: warp w reads TMEM lane quarter w & 3 (rows 32 (w & 3) ..), column half w >> 2
+#define POL_THREADS 288       // + 1 control warp whose lane 0 is the TMA producer and the MMA issuer. It must not share a warp
+                              // with threads that spin on an mbarrier: a diverged warp runs one path at a time and
+                              // mbarrier.try_wait suspends, which stalled the issuer ~3 us per chunk (profiles/r01c)
+#define POL_CTRL_TID 256
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// issue only; the destination registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Pipeline: thread 0 is both the TMA producer (weight chunk g + 1 is in flight while the MMAs of chunk g run; buffers
+// are recycled on the tcgen05.commit of the MMAs that read them) and the MMA issuer. full[b] / empty[b]: chunk g uses
+// buffer b = g & 1 and completion number g >> 1 of both barriers.
+__global__ void __launch_bounds__(POL_THREADS, 1)
 pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step,
                    int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
                    float* __restrict__ log_prob, float* __restrict__ logits_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB[2] = {smem + POL_A_BYTES, smem + POL_A_BYTES + POL_BCHUNK};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + POL_A_BYTES + 2 * POL_BCHUNK);   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint8_t* sB = smem + POL_A_BYTES;                                                  // [POL_NBUF][POL_BCHUNK]
+  float* sBias = reinterpret_cast<float*>(smem + POL_A_BYTES + POL_NBUF * POL_BCHUNK);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBias + POL_MAXBIAS);                 // [POL_NBUF]
+  uint64_t* empty = full + POL_NBUF;                                                 // [POL_NBUF]
+  uint64_t* layer_done = empty + POL_NBUF;                                           // completion number l = layer l accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * POL_TM;
 
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) {
+    for (int i = 0; i < POL_NBUF; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(layer_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // layer-0 A operand: normalised obs, bf16, canonical K-major layout (LBO = 128 B, SBO = Kp * 16 B)
+  __syncthreads();   // barriers initialised before the first bulk copy is issued
+  // producer state (thread 0): the next chunk to load, as (layer, chunk in layer, global index)
+  int ld_l = 0, ld_c = 0, ld_g = 0;
+  auto top_up = [&](int upto) {   // keep the weight stream `POL_NBUF - 1` chunks ahead of the chunk being multiplied
+    while (ld_l < P.n_layers && ld_g < upto) {
+      const PolicyLayer& Ln = P.L[ld_l];
+      const int b = ld_g % POL_NBUF;
+      if (ld_g >= POL_NBUF) mbar_wait(&empty[b], (uint32_t)((ld_g / POL_NBUF - 1) & 1));   // the MMAs that read this buffer are done
+      const uint32_t bytes = (uint32_t)(Ln.Np * Ln.Kc * 2);
+      mbar_expect_tx(&full[b], bytes);
+      bulk_g2s(sB + (size_t)b * POL_BCHUNK, reinterpret_cast<const uint8_t*>(P.w + Ln.w_off) + (size_t)ld_c * bytes, bytes, &full[b]);
+      ld_g++;
+      if (++ld_c == Ln.nchunks) { ld_c = 0; ld_l++; }
+    }
+  };
+  if (tid == POL_CTRL_TID) top_up(POL_NBUF - 1);   // the first weight chunks travel while the observations are staged
+  {
+    int nb = 0;
+    for (int l = 0; l < P.n_layers; l++) nb += P.L[l].Np;
+    for (int i = tid; i < nb; i += POL_THREADS) sBias[i] = __ldg(P.bias + i);
+  }
+  // layer-0 A operand: normalised obs, bf16, canonical K-major layout (LBO = 128 B, SBO = Kp * 16 B). A warp store
+  // covers 8 rows x 4 k-groups = 512 contiguous bytes (conflict-free); each lane converts 8 consecutive features.
   {
     const PolicyLayer& L0 = P.L[0];
     const uint32_t sbo = (uint32_t)L0.Kp * 16u;
-    for (int r = warp; r < POL_TM; r += 4) {
-      const int row = row0 + r;
-      for (int k = lane; k < L0.Kp; k += 32) {
-        float v = 0.f;
-        if (row < n_rows && k < L0.K) v = (obs[(size_t)row * P.obs_dim + k] - P.mean[k]) * P.inv_std[k];
-        const uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
-        *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16_rn(v);
+    const int kgroups = L0.Kp >> 3;
+    for (int rg = warp; rg < POL_TM / 8; rg += POL_THREADS / 32) {   // 16 row groups over 9 warps
+      const int r = rg * 8 + (lane & 7), row = row0 + r;
+      const float* orow = obs + (size_t)row * P.obs_dim;
+      for (int kg = lane >> 3; kg < kgroups; kg += 4) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int k = kg * 8 + i;
+          v[i] = (row < n_rows && k < L0.K) ? (__ldg(orow + k) - __ldg(P.mean + k)) * __ldg(P.inv_std + k) : 0.f;
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); pk[i] = *reinterpret_cast<const uint32_t*>(&h); }
+        *reinterpret_cast<uint4*>(sA + (uint32_t)rg * sbo + (uint32_t)kg * 128u + (uint32_t)(lane & 7) * 16u) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }
@@ -165,21 +248,17 @@ pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, un
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  int g = 0;   // global chunk counter: chunk g uses buffer g & 1, phase g >> 1 of bars[g & 1]
+  int g = 0;   // global chunk counter
   for (int l = 0; l < P.n_layers; l++) {
     const PolicyLayer& L = P.L[l];
-    const uint32_t a_sbo = (uint32_t)L.Kp * 16u, b_sbo = (uint32_t)L.Kc * 16u;
-    const int chunk_bytes = L.Np * L.Kc * 2;
-    for (int c = 0; c < L.nchunks; c++, g++) {
-      uint8_t* buf = sB[g & 1];
-      if (g >= 2) mbar_wait(&bars[g & 1], (uint32_t)(((g >> 1) - 1) & 1));   // MMAs that read this buffer are done
-      const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const uint8_t*>(P.w + L.w_off) + (size_t)c * chunk_bytes);
-      int4* dst = reinterpret_cast<int4*>(buf);
-      for (int i = tid; i < chunk_bytes / 16; i += POL_TM) dst[i] = __ldg(src + i);
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
+    if (tid == POL_CTRL_TID) {
+      const uint32_t a_sbo = (uint32_t)L.Kp * 16u, b_sbo = (uint32_t)L.Kc * 16u;
+      for (int c = 0; c < L.nchunks; c++) {
+        const int gc = g + c, bi = gc % POL_NBUF;
+        top_up(gc + POL_NBUF - 1);
+        mbar_wait(&full[bi], (uint32_t)((gc / POL_NBUF) & 1));
         tc_fence_after();
+        const uint8_t* buf = sB + (size_t)bi * POL_BCHUNK;
         const int nslices = L.Kc / 16;
         for (int s = 0; s < nslices; s++) {
           const int kslice = c * nslices + s;
@@ -191,62 +270,76 @@ pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, un
                       make_idesc(POL_TM, nn), (uint32_t)(kslice > 0));
           }
         }
-        umma_commit(&bars[g & 1]);
+        umma_commit(&empty[bi]);
       }
+      umma_commit(layer_done);
     }
-    // whole layer accumulated: wait for the last commit (MMAs retire in issue order)
-    mbar_wait(&bars[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
+    g += L.nchunks;
+    // whole layer accumulated. A barrier of its own: the warps that do not issue run a whole layer ahead of the
+    // empty[] phases, and a parity wait is only meaningful for the current or the previous phase.
+    if (warp < POL_EPI_THREADS / 32) {
+    mbar_wait(layer_done, (uint32_t)(l & 1));
     tc_fence_after();
-    const int r = tid, row = row0 + r;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const float* bias = P.bias + L.b_off;
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane, row = row0 + r;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const float* bias = sBias + L.b_off;
     if (l + 1 < P.n_layers) {
       const uint32_t sbo_next = (uint32_t)P.L[l + 1].Kp * 16u;   // == Np of this layer
-      for (int n0 = 0; n0 < L.Np; n0 += 8) {
-        float v[8];
-        tmem_ld8(trow + (uint32_t)n0, v);
-        uint32_t pk[4];
+      const int ncol = L.Np >> 1;                                  // this warp's column half (Np is a multiple of 16; hidden layers of 64)
+      for (int n00 = half * ncol; n00 < (half + 1) * ncol; n00 += 64) {   // ncol is a multiple of 64 (checked at create)... two loads per wait
+        float vv[64];
+        tmem_ld32_nowait(trow + (uint32_t)n00, vv);
+        tmem_ld32_nowait(trow + (uint32_t)n00 + 32u, vv + 32);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          float a = v[2 * i] + bias[n0 + 2 * i], b = v[2 * i + 1] + bias[n0 + 2 * i + 1];
-          a = (n0 + 2 * i < L.N) ? a / (1.f + __expf(-a)) : 0.f;          // SiLU (swish)
-          b = (n0 + 2 * i + 1 < L.N) ? b / (1.f + __expf(-b)) : 0.f;
-          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int j = 0; j < 8; j++) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int n = n00 + 8 * j + 2 * i;
+            float a = vv[8 * j + 2 * i] + bias[n], b = vv[8 * j + 2 * i + 1] + bias[n + 1];
+            a = (n < L.N) ? __fdividef(a, 1.f + __expf(-a)) : 0.f;          // SiLU (swish)
+            b = (n + 1 < L.N) ? __fdividef(b, 1.f + __expf(-b)) : 0.f;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          const uint32_t off = (uint32_t)(r >> 3) * sbo_next + (uint32_t)((n00 >> 3) + j) * 128u + (uint32_t)(r & 7) * 16u;
+          *reinterpret_cast<uint4*>(sA + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        const uint32_t off = (uint32_t)(r >> 3) * sbo_next + (uint32_t)(n0 >> 3) * 128u + (uint32_t)(r & 7) * 16u;
-        *reinterpret_cast<uint4*>(sA + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
     } else {
       // distribution head: logits = [loc | scale_raw], brax NormalTanhDistribution(min_std = 0.001)
-      float out[32];
-      for (int n0 = 0; n0 < L.Np && n0 < 32; n0 += 8) tmem_ld8(trow + (uint32_t)n0, out + n0);
-      if (row < n_rows) {
-        const int A = P.act_dim;
-        float lp = 0.f;
-        for (int j = 0; j < A; j++) {
-          const float loc = out[j] + bias[j], sr = out[A + j] + bias[A + j];
-          if (logits_out) { logits_out[(size_t)row * 2 * A + j] = loc; logits_out[(size_t)row * 2 * A + A + j] = sr; }
-          const float scale = (sr > 20.f ? sr : log1pf(expf(sr))) + 0.001f;
-          float e = 0.f;
-          if (!deterministic) e = eps_in ? eps_in[(size_t)row * A + j] : normal_draw(seed, step, (uint32_t)row, (uint32_t)j);
-          const float raw = loc + scale * e;
-          // log N(raw; loc, scale) - log|d tanh / d raw|, with log det = 2 (log 2 - raw - softplus(-2 raw))
-          const float m2 = -2.f * raw;
-          const float sp = m2 > 20.f ? m2 : log1pf(expf(m2));
-          lp += -0.5f * e * e - logf(scale) - 0.9189385332046727f - 2.f * (0.6931471805599453f - raw - sp);
-          action[(size_t)row * A + j] = tanhf(raw);
-          if (raw_action) raw_action[(size_t)row * A + j] = raw;
+      if (half == 0) {
+        float out[32];
+        tmem_ld32(trow, out);
+        if (row < n_rows) {
+          const int A = P.act_dim;
+          float lp = 0.f;
+          for (int j = 0; j < A; j++) {
+            const float loc = out[j] + bias[j], sr = out[A + j] + bias[A + j];
+            if (logits_out) { logits_out[(size_t)row * 2 * A + j] = loc; logits_out[(size_t)row * 2 * A + A + j] = sr; }
+            const float scale = (sr > 20.f ? sr : log1pf(expf(sr))) + 0.001f;
+            float e = 0.f;
+            if (!deterministic) e = eps_in ? eps_in[(size_t)row * A + j] : normal_draw(seed, step, (uint32_t)row, (uint32_t)j);
+            const float raw = loc + scale * e;
+            // log N(raw; loc, scale) - log|d tanh / d raw|, with log det = 2 (log 2 - raw - softplus(-2 raw))
+            const float m2 = -2.f * raw;
+            const float sp = m2 > 20.f ? m2 : log1pf(expf(m2));
+            lp += -0.5f * e * e - logf(scale) - 0.9189385332046727f - 2.f * (0.6931471805599453f - raw - sp);
+            action[(size_t)row * A + j] = tanhf(raw);
+            if (raw_action) raw_action[(size_t)row * A + j] = raw;
+          }
+          if (log_prob) log_prob[row] = lp;
         }
-        if (log_prob) log_prob[row] = lp;
       }
       tc_fence_before();
-      __syncthreads();
     }
+    }   // epilogue warps
+    __syncthreads();
+    tc_fence_after();
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
@@ -313,6 +406,9 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
     L.w_off = w_off; L.b_off = b_off;
     w_off += (size_t)L.Np * L.Kp; b_off += L.Np;
   }
+  for (int l = 0; l + 1 < n_layers; l++)
+    if (P.L[l].Np % 128 != 0) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: hidden widths must be multiples of 128"); }
+  if (b_off > POL_MAXBIAS) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: total layer width above 1024"); }
   if (P.L[n_layers - 1].Np > 32 || sizes[n_layers] % 2) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: head must be 2 * act_dim <= 32"); }
   p->w_elems = w_off; p->b_elems = b_off;
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->w_dev, w_off * 2) != cudaSuccess || cudaMalloc(&p->bias_dev, b_off * 4) != cudaSuccess ||
@@ -371,7 +467,7 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
   if (!p || !obs || !action || n <= 0) return pfail(PGTT_ERR_ARG, "pgtt_policy_act: null argument or n <= 0");
   if (!p->has_params) return pfail(PGTT_ERR_STATE, "pgtt_policy_act: pgtt_policy_set_params first");
   const int blocks = (n + POL_TM - 1) / POL_TM;
-  pgtt_policy_kernel<<<blocks, POL_TM, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
+  pgtt_policy_kernel<<<blocks, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
                                                                         deterministic, eps, action, raw_action, log_prob, logits);
   PCUDA(cudaGetLastError());
   p->launches++;
