@@ -131,11 +131,11 @@ __device__ float normal_draw(uint64_t seed, uint64_t step, uint32_t row, uint32_
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
-#define POL_EPI_THREADS 256   // 8 epilogue warps: warp w reads TMEM lane quarter w & 3 (rows 32 (w & 3) ..), column half w >> 2
-#define POL_THREADS 288       // + 1 control warp whose lane 0 is the TMA producer and the MMA issuer. It must not share a warp
+#define POL_EPI_THREADS 512   // 16 epilogue warps: warp w reads TMEM lane quarter w & 3 (rows 32 (w & 3) ..), column quarter w >> 2
+#define POL_THREADS 544       // + 1 control warp whose lane 0 is the TMA producer and the MMA issuer. It must not share a warp
                               // with threads that spin on an mbarrier: a diverged warp runs one path at a time and
                               // mbarrier.try_wait suspends, which stalled the issuer ~3 us per chunk (profiles/r01c)
-#define POL_CTRL_TID 256
+#define POL_CTRL_TID 512
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -225,7 +225,7 @@ pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, un
     const PolicyLayer& L0 = P.L[0];
     const uint32_t sbo = (uint32_t)L0.Kp * 16u;
     const int kgroups = L0.Kp >> 3;
-    for (int rg = warp; rg < POL_TM / 8; rg += POL_THREADS / 32) {   // 16 row groups over 9 warps
+    for (int rg = warp; rg < POL_TM / 8; rg += POL_THREADS / 32) {   // 16 row groups, one per warp
       const int r = rg * 8 + (lane & 7), row = row0 + r;
       const float* orow = obs + (size_t)row * P.obs_dim;
       for (int kg = lane >> 3; kg < kgroups; kg += 4) {
@@ -280,61 +280,64 @@ pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, un
     if (warp < POL_EPI_THREADS / 32) {
     mbar_wait(layer_done, (uint32_t)(l & 1));
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;
     const int r = q * 32 + lane, row = row0 + r;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const float* bias = sBias + L.b_off;
     if (l + 1 < P.n_layers) {
       const uint32_t sbo_next = (uint32_t)P.L[l + 1].Kp * 16u;   // == Np of this layer
-      const int ncol = L.Np >> 1;                                  // this warp's column half (Np is a multiple of 16; hidden layers of 64)
-      for (int n00 = half * ncol; n00 < (half + 1) * ncol; n00 += 64) {   // ncol is a multiple of 64 (checked at create)... two loads per wait
-        float vv[64];
-        tmem_ld32_nowait(trow + (uint32_t)n00, vv);
-        tmem_ld32_nowait(trow + (uint32_t)n00 + 32u, vv + 32);
-        tmem_ld_wait();
+      const int ncol = L.Np >> 2;                                  // this warp's column quarter (Np is a multiple of 128)
+      for (int n0 = cq * ncol; n0 < (cq + 1) * ncol; n0 += 32) {
+        float vv[32];
+        tmem_ld32(trow + (uint32_t)n0, vv);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
           uint32_t pk[4];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const int n = n00 + 8 * j + 2 * i;
+            const int n = n0 + 8 * j + 2 * i;
             float a = vv[8 * j + 2 * i] + bias[n], b = vv[8 * j + 2 * i + 1] + bias[n + 1];
             a = (n < L.N) ? __fdividef(a, 1.f + __expf(-a)) : 0.f;          // SiLU (swish)
             b = (n + 1 < L.N) ? __fdividef(b, 1.f + __expf(-b)) : 0.f;
             const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
             pk[i] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          const uint32_t off = (uint32_t)(r >> 3) * sbo_next + (uint32_t)((n00 >> 3) + j) * 128u + (uint32_t)(r & 7) * 16u;
+          const uint32_t off = (uint32_t)(r >> 3) * sbo_next + (uint32_t)((n0 >> 3) + j) * 128u + (uint32_t)(r & 7) * 16u;
           *reinterpret_cast<uint4*>(sA + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       fence_proxy_async();
       tc_fence_before();
     } else {
-      // distribution head: logits = [loc | scale_raw], brax NormalTanhDistribution(min_std = 0.001)
-      if (half == 0) {
-        float out[32];
-        tmem_ld32(trow, out);
-        if (row < n_rows) {
-          const int A = P.act_dim;
-          float lp = 0.f;
-          for (int j = 0; j < A; j++) {
-            const float loc = out[j] + bias[j], sr = out[A + j] + bias[A + j];
-            if (logits_out) { logits_out[(size_t)row * 2 * A + j] = loc; logits_out[(size_t)row * 2 * A + A + j] = sr; }
-            const float scale = (sr > 20.f ? sr : log1pf(expf(sr))) + 0.001f;
-            float e = 0.f;
-            if (!deterministic) e = eps_in ? eps_in[(size_t)row * A + j] : normal_draw(seed, step, (uint32_t)row, (uint32_t)j);
-            const float raw = loc + scale * e;
-            // log N(raw; loc, scale) - log|d tanh / d raw|, with log det = 2 (log 2 - raw - softplus(-2 raw))
-            const float m2 = -2.f * raw;
-            const float sp = m2 > 20.f ? m2 : log1pf(expf(m2));
-            lp += -0.5f * e * e - logf(scale) - 0.9189385332046727f - 2.f * (0.6931471805599453f - raw - sp);
-            action[(size_t)row * A + j] = tanhf(raw);
-            if (raw_action) raw_action[(size_t)row * A + j] = raw;
-          }
-          if (log_prob) log_prob[row] = lp;
+      // distribution head: logits = [loc | scale_raw], brax NormalTanhDistribution(min_std = 0.001). The four warps of a
+      // lane quarter split the actions; log-prob partial sums meet in shared memory (sA is free: the last MMAs are done)
+      float out[32];
+      tmem_ld32(trow, out);
+      const int A = P.act_dim, per = (A + 3) >> 2;
+      float* lp_part = reinterpret_cast<float*>(sA);            // [4][POL_TM]
+      float lp = 0.f;
+      if (row < n_rows) {
+        for (int j = cq * per; j < (cq + 1) * per && j < A; j++) {
+          float ol = 0.f, os = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i++) { ol = (i == j) ? out[i] : ol; os = (i == A + j) ? out[i] : os; }
+          const float loc = ol + bias[j], sr = os + bias[A + j];
+          if (logits_out) { logits_out[(size_t)row * 2 * A + j] = loc; logits_out[(size_t)row * 2 * A + A + j] = sr; }
+          const float scale = (sr > 20.f ? sr : log1pf(expf(sr))) + 0.001f;
+          float e = 0.f;
+          if (!deterministic) e = eps_in ? eps_in[(size_t)row * A + j] : normal_draw(seed, step, (uint32_t)row, (uint32_t)j);
+          const float raw = loc + scale * e;
+          // log N(raw; loc, scale) - log|d tanh / d raw|, with log det = 2 (log 2 - raw - softplus(-2 raw))
+          const float m2 = -2.f * raw;
+          const float sp = m2 > 20.f ? m2 : log1pf(expf(m2));
+          lp += -0.5f * e * e - logf(scale) - 0.9189385332046727f - 2.f * (0.6931471805599453f - raw - sp);
+          action[(size_t)row * A + j] = tanhf(raw);
+          if (raw_action) raw_action[(size_t)row * A + j] = raw;
         }
       }
+      lp_part[cq * POL_TM + r] = lp;
+      asm volatile("bar.sync 1, %0;" ::"r"(POL_EPI_THREADS) : "memory");
+      if (cq == 0 && row < n_rows && log_prob) log_prob[row] = ((lp_part[r] + lp_part[POL_TM + r]) + lp_part[2 * POL_TM + r]) + lp_part[3 * POL_TM + r];
       tc_fence_before();
     }
     }   // epilogue warps
