@@ -17,6 +17,10 @@
 
 #define QENV 8
 #define QCAND 8            // penetrating boxes remembered per foot
+#define QPEN 10            // near-list capacities per foot (overflow falls back to the full scan)
+#define QCEN 32
+#define Q_MARGIN 0.12f     // foot travel within one control step covered by the near lists (checked every substep)
+#define Q_RCEN 0.9f        // broad-phase thresholds below Q_RCEN^2 are ranked from the centre lists
 #define Q_INF __int_as_float(0x7f800000)
 
 // ----------------------------------------------------------------------------------------------
@@ -51,6 +55,7 @@ struct QShared {
   // lane-private columns ([k][lane]: conflict-free, no synchronisation needed)
   float cand_dist[QCAND][32], cand_cd2[QCAND][32];
   int cand_box[QCAND][32], cand_rank[QCAND][32];
+  int pen_list[QPEN][32], cen_list[QCEN][32];
 };
 
 DEV void q_stage_consts(QShared& S, int lane) {
@@ -472,7 +477,32 @@ DEV void q_collide_plane(QGeo& GP, const QKin& K, const QModel& M, int g) {
   GP.mu = fmaxf(GC.foot_mu, M.floor_mu);
 }
 
-DEV void q_collide_boxes(QGeo& GX, QShared& S, const QKin& K, const QModel& M, int lane, int g, int qbase) {
+// Per control step and foot: the boxes whose SURFACE can come within the foot radius (penetration tests) and the boxes
+// whose CENTRE can come within Q_RCEN (broad-phase ranks) while the foot travels at most Q_MARGIN from where the lists
+// were built. Both are conservative supersets, so scanning them gives bit-identical contact bookkeeping to scanning all
+// 100 boxes; travel beyond the margin, list overflow or a threshold above Q_RCEN^2 falls back to the full scan.
+struct QNear { float f0[3]; int npen, ncen; bool over; };
+
+DEV void q_build_near(QNear& Nr, QShared& S, const QModel& M, const float* foot, int lane) {
+  const int nb = GC.n_boxes;
+  const float4* bp = reinterpret_cast<const float4*>(M.box);
+  const float rp = (GC.foot_r + Q_MARGIN) * 1.001f, rc = (Q_RCEN + Q_MARGIN) * 1.001f;
+  const float rp2 = rp * rp, rc2 = rc * rc;
+  int npen = 0, ncen = 0;
+#pragma unroll 4
+  for (int k = 0; k < nb; k++) {
+    const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
+    const float dx = b0.x - foot[0], dy = b0.y - foot[1], dz = b0.z - foot[2];
+    const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
+    const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
+    if (e0 * e0 + e1 * e1 + e2 * e2 < rp2) { if (npen < QPEN) S.pen_list[npen][lane] = k; npen++; }
+    if (dx * dx + dy * dy + dz * dz < rc2) { if (ncen < QCEN) S.cen_list[ncen][lane] = k; ncen++; }
+  }
+  Nr.f0[0] = foot[0]; Nr.f0[1] = foot[1]; Nr.f0[2] = foot[2];
+  Nr.npen = npen; Nr.ncen = ncen; Nr.over = (npen > QPEN) || (ncen > QCEN);
+}
+
+DEV void q_collide_boxes(QGeo& GX, QNear& Nr, bool build, QShared& S, const QKin& K, const QModel& M, int lane, int g, int qbase) {
   GX.dist = 1.f; GX.leg = 0; GX.box = -2; GX.mu = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; i++) GX.pos[i] = 0.f;
@@ -480,24 +510,34 @@ DEV void q_collide_boxes(QGeo& GX, QShared& S, const QKin& K, const QModel& M, i
   for (int i = 0; i < 9; i++) GX.fr[i] = 0.f;
   const int nb = GC.n_boxes;
   if (nb <= 0) return;
+  if (build) q_build_near(Nr, S, M, K.foot, lane);
   const float r = GC.foot_r, r2 = r * r * 1.0001f;   // conservative pre-filter; the exact test runs only where it passes
   const float fx = K.foot[0], fy = K.foot[1], fz = K.foot[2];
   const float4* bp = reinterpret_cast<const float4*>(M.box);
+  bool lists_ok;
+  {
+    const float tx = fx - Nr.f0[0], ty = fy - Nr.f0[1], tz = fz - Nr.f0[2];
+    lists_ok = !Nr.over && (tx * tx + ty * ty + tz * tz <= Q_MARGIN * Q_MARGIN);
+  }
+  const bool full = GC.quad_fullscan || any_lane(!lists_ok);
   int ncand = 0;
-#pragma unroll 4
-  for (int k = 0; k < nb; k++) {
-    const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
-    const float dx = b0.x - fx, dy = b0.y - fy, dz = b0.z - fz;
-    const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
-    const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
-    if (e0 * e0 + e1 * e1 + e2 * e2 < r2) {
-      const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float l[3], pt[3];
-      const float dist = sphere_box_local(bx, K.foot, r, l, pt);
-      if (dist < 0.f && ncand < QCAND) {
-        S.cand_box[ncand][lane] = k; S.cand_dist[ncand][lane] = dist; S.cand_cd2[ncand][lane] = q_sqdist3(dx, dy, dz);
-        S.cand_rank[ncand][lane] = g * NBOX + k;
-        ncand++;
+  {
+    const int cnt = full ? nb : Nr.npen;
+    for (int i = 0; i < cnt; i++) {
+      const int k = full ? i : S.pen_list[i][lane];
+      const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
+      const float dx = b0.x - fx, dy = b0.y - fy, dz = b0.z - fz;
+      const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
+      const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
+      if (e0 * e0 + e1 * e1 + e2 * e2 < r2) {
+        const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float l[3], pt[3];
+        const float dist = sphere_box_local(bx, K.foot, r, l, pt);
+        if (dist < 0.f && ncand < QCAND) {
+          S.cand_box[ncand][lane] = k; S.cand_dist[ncand][lane] = dist; S.cand_cd2[ncand][lane] = q_sqdist3(dx, dy, dz);
+          S.cand_rank[ncand][lane] = g * NBOX + k;
+          ncand++;
+        }
       }
     }
   }
@@ -512,11 +552,13 @@ DEV void q_collide_boxes(QGeo& GX, QShared& S, const QKin& K, const QModel& M, i
       const bool have = c < ncand;
       const float myt = have ? S.cand_cd2[c][lane] : -1.f;
       const int myid = have ? g * NBOX + S.cand_box[c][lane] : 0;
+      const bool full2 = full || any_lane(have && !(myt < Q_RCEN * Q_RCEN));
       float t[4]; int id[4], cnt[4];
 #pragma unroll
       for (int s = 0; s < 4; s++) { t[s] = shfl(myt, qbase | s); id[s] = shfl(myid, qbase | s); cnt[s] = 0; }
-#pragma unroll 4
-      for (int k = 0; k < nb; k++) {
+      const int n2 = full2 ? nb : Nr.ncen;
+      for (int i = 0; i < n2; i++) {
+        const int k = full2 ? i : S.cen_list[i][lane];
         const float4 b0 = ldg4(bp + 2 * k);
         const float v = q_sqdist3(b0.x - fx, b0.y - fy, b0.z - fz);
         const int idk = g * NBOX + k;
@@ -1086,7 +1128,7 @@ DEV void q_euler(QState& X, const QVec& qacc) {
 struct QFwd { QGeo GP, GX; float actf[3]; int niter; };
 
 template <bool DBG>
-DEV void q_forward(QFwd& O, QSol& S, QSens& Z, QShared& Sh, const QState& X, const QModel& M, const LegC& L, bool sens, float* dbg, int lane, int g, int qbase) {
+DEV void q_forward(QFwd& O, QSol& S, QSens& Z, QNear& Nr, bool build_near, QShared& Sh, const QState& X, const QModel& M, const LegC& L, bool sens, float* dbg, int lane, int g, int qbase) {
   QMass Mm;
   QVec qs, qas;
   QCon CP, CX;
@@ -1095,7 +1137,7 @@ DEV void q_forward(QFwd& O, QSol& S, QSens& Z, QShared& Sh, const QState& X, con
     QKin K;
     q_kinematics(K, X, M, L);
     q_collide_plane(O.GP, K, M, g);
-    q_collide_boxes(O.GX, Sh, K, M, lane, g, qbase);
+    q_collide_boxes(O.GX, Nr, build_near, Sh, K, M, lane, g, qbase);
     float xi[4][3];
     q_com_inertia_cdof(K, M, L, DBG ? xi : nullptr);
     q_mass_matrix(Mm, K, M);
@@ -1374,11 +1416,12 @@ DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, i
   QFwd O;
   QSol S;
   QSens Z;
+  QNear Nr;
   int niter[4] = {0, 0, 0, 0};
   const int nsub = GC.n_substeps;
 #pragma unroll 1
   for (int s = 0; s < nsub; s++) {
-    q_forward<false>(O, S, Z, Sh, X, M, L, s == nsub - 1, nullptr, lane, g, qbase);
+    q_forward<false>(O, S, Z, Nr, s == 0, Sh, X, M, L, s == nsub - 1, nullptr, lane, g, qbase);
 #pragma unroll
     for (int i = 0; i < 4; i++) if (i == s) niter[i] = O.niter;
     q_euler(X, S.qacc);
@@ -1614,9 +1657,9 @@ DEV void q_env_debug_forward(QShared& Sh, const EnvBuffers& B, float* out_all, i
   for (int t = 0; t < 3; t++) X.ctrl[t] = B.ctrl[env * NU + L.act[t]];
   if (ok) for (int i = g; i < 44 * 18; i += 4) o[DBG_EFC_J + i] = 0.f;
   syncwarp();
-  QFwd O; QSol S; QSens Z;
+  QFwd O; QSol S; QSens Z; QNear Nr;
   // surplus quads shadow the last env: they write the same values to the same record
-  q_forward<true>(O, S, Z, Sh, X, M, L, true, o, lane, g, qbase);
+  q_forward<true>(O, S, Z, Nr, true, Sh, X, M, L, true, o, lane, g, qbase);
   if (g == 0) {
     for (int a = 0; a < 6; a++) o[DBG_QACC + a] = S.qacc.b[a];
     for (int i = 0; i < 3; i++) {

@@ -8,7 +8,8 @@ import pytest
 
 def make_env(kind, model, cfg, n, **kw):
     base, _, gen = kind.partition("-")
-    os.environ["PGTT_KERNEL"] = gen or "warp"
+    os.environ["PGTT_KERNEL"] = "quad" if gen.startswith("quad") else "warp"
+    os.environ["PGTT_QUAD_FULLSCAN"] = "1" if gen == "quadfull" else "0"
     try:
         if base == "emu":
             import emu_backend
@@ -17,7 +18,8 @@ def make_env(kind, model, cfg, n, **kw):
         return AbiEnv(model, cfg, n, backend="torch", **kw)
     finally:
         os.environ.pop("PGTT_KERNEL", None)
+        os.environ.pop("PGTT_QUAD_FULLSCAN", None)
 
 
-BACKENDS = [pytest.param("emu", id="emu"), pytest.param("emu-quad", id="emu-quad"),
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("emu-quad", id="emu-quad"), pytest.param("emu-quadfull", id="emu-quadfull"),
             pytest.param("cuda", id="cuda", marks=pytest.mark.gpu), pytest.param("cuda-quad", id="cuda-quad", marks=pytest.mark.gpu)]
