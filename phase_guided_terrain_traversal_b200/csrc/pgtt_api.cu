@@ -249,7 +249,7 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
 #ifndef PGTT_HOST_EMU
   cudaStream_t st = (cudaStream_t)stream;
   if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
-    int qw = e->N >= 8192 ? QWARPS_MAX : 1;   // lockstep CTAs once there is more than one warp per scheduler
+    int qw = e->N >= 5000 ? QWARPS_MAX : 1;   // lockstep CTAs once there is more than one warp per scheduler
     if (const char* s = getenv("PGTT_QUAD_WARPS")) { const int v = atoi(s); if (v >= 1 && v <= QWARPS_MAX) qw = v; }
     const int qwarps = (e->N + QENV - 1) / QENV, qblocks = (qwarps + qw - 1) / qw;
     const size_t qsmem = qw * ((sizeof(QShared) + 15) / 16 * 16);
@@ -345,10 +345,10 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
 #endif
   pgtt_env* e = new pgtt_env();
   e->device = device; e->N = num_envs; e->wpb = pick_warps_per_block(num_envs); e->terrain_dev = nullptr; e->n_terrains = 0; e->launches = 0; e->randomized = false;
-  // Kernel generation for step / debug-forward. Measured on B200 (profiles/r01c): with <= 8192 envs per GPU the
-  // warp-per-env kernel is faster (the quad kernel has one latency-bound warp per scheduler there); from ~12k envs
-  // per GPU the quad kernel in 8-warp lockstep CTAs wins. PGTT_KERNEL=warp|quad overrides.
-  e->quad = num_envs >= 12288;
+  // Kernel generation for step / debug-forward. Measured on B200 (profiles/r01c): the quad kernel needs ~0.7 ms per
+  // step up to 8192 envs (one or two latency-bound warps per scheduler) and the warp-per-env kernel 0.125 us per env,
+  // so the quad kernel wins from ~4.8k envs per GPU (1.15x at 6144, 1.45x at 8192). PGTT_KERNEL=warp|quad overrides.
+  e->quad = num_envs >= 5000;
   if (const char* k = getenv("PGTT_KERNEL")) e->quad = strcmp(k, "quad") == 0;
   ModelConst& c = e->mc;
   memset(&c, 0, sizeof(c));

@@ -843,27 +843,46 @@ DEV void q_hessian_factor(QFac& F, const QMass& Mm, const QForce& Fo, const QCon
 
 struct QLSPoint { float alpha, cost, d0, d1; };
 
-DEV QLSPoint q_ls_eval(float alpha, const QCon& CP, const QCon& CX, const QLim& Lm, const float (*qP)[3], const float (*qX)[3], const float (*qL)[3], const float* qg) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+// NA line-search points at once (the three candidates of one bracketing iteration are independent: evaluating them
+// together triples the instruction-level parallelism of the row loop and of the quad reductions). Inactive rows have
+// jaref = jv = 0, so their test is false without looking at the active flag.
+template <int NA>
+DEV void q_ls_eval(QLSPoint* out, const float* alpha, const QCon& CP, const QCon& CX, const QLim& Lm, const float (*qP)[3], const float (*qX)[3],
+                   const float (*qL)[3], const float* qg, bool anyX, bool anyL) {
+  float s[NA][3];
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    if (CP.active && (CP.jaref[e] + alpha * CP.jv[e] < 0.f)) { s0 += qP[e][0]; s1 += qP[e][1]; s2 += qP[e][2]; }
-    if (CX.active && (CX.jaref[e] + alpha * CX.jv[e] < 0.f)) { s0 += qX[e][0]; s1 += qX[e][1]; s2 += qX[e][2]; }
+  for (int a = 0; a < NA; a++) { s[a][0] = 0.f; s[a][1] = 0.f; s[a][2] = 0.f; }
+#pragma unroll
+  for (int e = 0; e < 4; e++)
+#pragma unroll
+    for (int a = 0; a < NA; a++)
+      if (CP.jaref[e] + alpha[a] * CP.jv[e] < 0.f) { s[a][0] += qP[e][0]; s[a][1] += qP[e][1]; s[a][2] += qP[e][2]; }
+  if (anyX) {
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int a = 0; a < NA; a++)
+        if (CX.jaref[e] + alpha[a] * CX.jv[e] < 0.f) { s[a][0] += qX[e][0]; s[a][1] += qX[e][1]; s[a][2] += qX[e][2]; }
+  }
+  if (anyL) {
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+      for (int a = 0; a < NA; a++)
+        if (Lm.jaref[t] + alpha[a] * Lm.jv[t] < 0.f) { s[a][0] += qL[t][0]; s[a][1] += qL[t][1]; s[a][2] += qL[t][2]; }
   }
 #pragma unroll
-  for (int t = 0; t < 3; t++)
-    if (Lm.active[t] && (Lm.jaref[t] + alpha * Lm.jv[t] < 0.f)) { s0 += qL[t][0]; s1 += qL[t][1]; s2 += qL[t][2]; }
-  s0 = qsum(s0) + qg[0]; s1 = qsum(s1) + qg[1]; s2 = qsum(s2) + qg[2];
-  QLSPoint p;
-  p.alpha = alpha;
-  p.cost = alpha * alpha * s2 + alpha * s1 + s0;
-  p.d0 = 2.f * alpha * s2 + s1;
-  p.d1 = 2.f * s2 + (s2 == 0.f ? PGTT_MINVAL : 0.f);
-  return p;
+  for (int a = 0; a < NA; a++) {
+    const float s0 = qsum(s[a][0]) + qg[0], s1 = qsum(s[a][1]) + qg[1], s2 = qsum(s[a][2]) + qg[2];
+    out[a].alpha = alpha[a];
+    out[a].cost = alpha[a] * alpha[a] * s2 + alpha[a] * s1 + s0;
+    out[a].d0 = 2.f * alpha[a] * s2 + s1;
+    out[a].d1 = 2.f * s2 + (s2 == 0.f ? PGTT_MINVAL : 0.f);
+  }
 }
 
 // `live`: this env still iterates (envs that converged ride along without changing state)
-DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, const QVec& search, const QVec& qs, bool live, int qbase, bool anyX) {
+DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, const QVec& search, const QVec& qs, bool live, int qbase, bool anyX, bool anyL) {
   QVec mv;
   q_mul(mv, Mm, search);
   {
@@ -900,8 +919,13 @@ DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, co
   for (int t = 0; t < 3; t++) {
     qL[t][0] = 0.5f * Lm.jaref[t] * Lm.jaref[t] * Lm.D[t]; qL[t][1] = Lm.jv[t] * Lm.jaref[t] * Lm.D[t]; qL[t][2] = 0.5f * Lm.jv[t] * Lm.jv[t] * Lm.D[t];
   }
-  const QLSPoint p0 = q_ls_eval(0.f, CP, CX, Lm, qP, qX, qL, qg);
-  const QLSPoint l0 = q_ls_eval(p0.alpha - p0.d0 / p0.d1, CP, CX, Lm, qP, qX, qL, qg);
+  QLSPoint p0, l0;
+  {
+    const float a0 = 0.f;
+    q_ls_eval<1>(&p0, &a0, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);
+    const float a1 = p0.alpha - p0.d0 / p0.d1;
+    q_ls_eval<1>(&l0, &a1, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);
+  }
   const bool lesser = l0.d0 < p0.d0;
   QLSPoint hi = lesser ? p0 : l0, lo = lesser ? l0 : p0;
   bool swap = true;
@@ -913,9 +937,10 @@ DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, co
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (cta_all(done)) break;
-    const QLSPoint lo_next = q_ls_eval(lo.alpha - lo.d0 / lo.d1, CP, CX, Lm, qP, qX, qL, qg);
-    const QLSPoint hi_next = q_ls_eval(hi.alpha - hi.d0 / hi.d1, CP, CX, Lm, qP, qX, qL, qg);
-    const QLSPoint mid = q_ls_eval(0.5f * (lo.alpha + hi.alpha), CP, CX, Lm, qP, qX, qL, qg);
+    QLSPoint pts[3];
+    const float al3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+    q_ls_eval<3>(pts, al3, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);
+    const QLSPoint lo_next = pts[0], hi_next = pts[1], mid = pts[2];
     if (!done) {
       const bool s_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
       if (s_lo_next) lo = lo_next;
@@ -947,6 +972,7 @@ DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, co
 DEV int q_solve_constraints(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, const QVec& qs, const QVec& qas, const QVec& warm,
                             int g, int qbase) {
   const bool anyX = any_lane(CX.active);
+  const bool anyL = any_lane(Lm.active[0] | Lm.active[1] | Lm.active[2]);
   QForce Fo;
   QFac F = {};
   QVec keep_q = warm, keep_Ma = warm;
@@ -1021,7 +1047,7 @@ DEV int q_solve_constraints(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& 
     for (int a = 0; a < 6; a++) search.b[a] = -search.b[a];
 #pragma unroll
     for (int t = 0; t < 3; t++) search.l[t] = -search.l[t];
-    q_linesearch(S, CP, CX, Lm, Mm, search, qs, live, qbase, anyX);
+    q_linesearch(S, CP, CX, Lm, Mm, search, qs, live, qbase, anyX, anyL);
     if (live) niter++;
   }
   return niter;
