@@ -1,0 +1,85 @@
+"""`python -m phase_guided_terrain_traversal_b200.train` - the call sequence of training/train.py:102-268 over the
+B200-native env, rollout collector and PPO learner (same flags as training/train.py:285-296).
+
+    python -m phase_guided_terrain_traversal_b200.train --task_name stairs --terrain_file level1 --num_envs 4096 \
+        --num_timesteps 10000000 [--out policy_out]
+    torchrun --nproc-per-node 8 -m phase_guided_terrain_traversal_b200.train --num_envs 65536 --batch_size 2048 ...
+
+Under torchrun every rank owns `num_envs / world` envs (index sharding, sharding.py); gradients and observation
+statistics are all-reduced over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import functools
+import os
+import time
+
+import numpy as np
+
+
+def run_training(args):
+    import torch
+    import torch.distributed as dist
+    from . import ppo, registry, sharding, terrain, wrapper
+    from .go2 import joystick_pgtt, randomize, randomize_simple
+    from .go2.configs import default_config
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    env_name = "Go2"
+    registry.register_environment(env_name, functools.partial(joystick_pgtt.Joystick, task=args.task_name, device=local), default_config)   # train.py:115-116
+    env_cfg = default_config()                                                                                       # train.py:119-129
+    env_cfg.command_config.u_max = [0.6, 0.6, 1.0]
+    env_cfg.command_config.u_min = [-0.6, -0.6, -1.0]
+    env_cfg.gait_freq = [1, 3]
+    env = registry.load(env_name, config=env_cfg)
+    if args.task_name == "stairs":                                                                                   # train.py:165-170
+        matrix = terrain.load_terrain(args.terrain_file)
+        registry._randomizer[env_name] = functools.partial(randomize.domain_randomize, terrain_matrix=matrix)
+    else:
+        registry._randomizer[env_name] = randomize_simple.domain_randomize
+    cfg = ppo.PPOConfig(num_timesteps=args.num_timesteps, episode_length=env_cfg.episode_length, num_minibatches=args.num_minibatches,
+                        discounting=args.discount, learning_rate=args.learning_rate, num_envs=args.num_envs, batch_size=args.batch_size,
+                        seed=args.seed)                                                                                # train.py:135-161
+    keys = sharding.shard_keys(args.seed, args.num_envs, rank, world)
+    t0 = time.time()
+
+    def progress(num_steps, metrics):                                                                                # train.py:189-229
+        if rank == 0:
+            print(f"steps {num_steps:>12d}  reward/step {metrics['reward_per_step']:.5f}  done-rate {metrics['episode_done_rate']:.4f}  "
+                  f"loss {metrics['total_loss']:.4f}  entropy {metrics['entropy']:.3f}  {num_steps / (time.time() - t0):,.0f} env-steps/s", flush=True)
+
+    trainer = ppo.train(environment=env, wrap_env_fn=wrapper.wrap_for_brax_training, randomization_fn=registry.get_domain_randomizer(env_name),
+                        rng_keys=keys, cfg=cfg, progress_fn=progress)
+    if rank == 0 and args.out:
+        trainer.save(args.out)                                                                                       # model.save_params, train.py:266
+        print(f"saved {args.out} (layout of deploy/policy_net.py:6-33)")
+    if world > 1:
+        dist.destroy_process_group()
+    return trainer
+
+
+def main():
+    p = argparse.ArgumentParser(description="Train PPO on the B200-native GO2 PGTT env")
+    p.add_argument("--method", type=str, default="pgtt")
+    p.add_argument("--task_name", type=str, default="stairs")
+    p.add_argument("--terrain_file", type=str, default="level1")
+    p.add_argument("--num_envs", type=int, default=4096)
+    p.add_argument("--batch_size", type=int, default=256)
+    p.add_argument("--discount", type=float, default=0.97)
+    p.add_argument("--learning_rate", type=float, default=3e-4)
+    p.add_argument("--num_minibatches", type=int, default=32)
+    p.add_argument("--num_timesteps", type=int, default=1)
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--out", type=str, default=None)
+    args = p.parse_args()
+    if args.method != "pgtt":
+        raise SystemExit("only --method pgtt is built (the baseline task variant is a SURVEY 8f-3 'next' row)")
+    run_training(args)
+
+
+if __name__ == "__main__":
+    main()

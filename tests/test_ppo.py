@@ -1,0 +1,143 @@
+"""PPO learner: pure functions against independent restatements on CPU; the trainer end to end on the GPU."""
+import math
+
+import numpy as np
+import pytest
+
+
+def gae_numpy(trunc, term, rew, val, boot, lam, gamma):
+    """Loop form of generalized advantage estimation with brax's truncation handling."""
+    T, B = rew.shape
+    vs = np.zeros((T, B)); adv = np.zeros((T, B))
+    v_next = np.concatenate([val[1:], boot[None]], 0)
+    acc = np.zeros(B)
+    for t in reversed(range(T)):
+        mask = 1.0 - trunc[t]
+        delta = (rew[t] + gamma * (1 - term[t]) * v_next[t] - val[t]) * mask
+        acc = delta + gamma * (1 - term[t]) * mask * lam * acc
+        vs[t] = acc + val[t]
+    vs_next = np.concatenate([vs[1:], boot[None]], 0)
+    adv = (rew + gamma * (1 - term) * vs_next - val) * (1 - trunc)
+    return vs, adv
+
+
+def test_compute_gae_matches_loop_form():
+    import torch
+    from phase_guided_terrain_traversal_b200.ppo import compute_gae
+    g = np.random.default_rng(0)
+    T, B = 20, 37
+    trunc = (g.random((T, B)) < 0.05).astype(np.float64)
+    term = ((g.random((T, B)) < 0.05) & (trunc == 0)).astype(np.float64)
+    rew, val, boot = g.normal(size=(T, B)), g.normal(size=(T, B)), g.normal(size=B)
+    vs, adv = compute_gae(*(torch.from_numpy(x) for x in (trunc, term, rew, val, boot)), 0.95, 0.97)
+    vs_n, adv_n = gae_numpy(trunc, term, rew, val, boot, 0.95, 0.97)
+    assert np.allclose(vs.numpy(), vs_n, atol=1e-12) and np.allclose(adv.numpy(), adv_n, atol=1e-12)
+    # no termination / truncation, lambda = 1: advantages are discounted returns minus values
+    z = np.zeros((T, B))
+    vs1, adv1 = compute_gae(*(torch.from_numpy(x) for x in (z, z, rew, val, boot)), 1.0, 0.9)
+    ret = np.zeros((T, B)); acc = boot.copy()
+    for t in reversed(range(T)):
+        acc = rew[t] + 0.9 * acc; ret[t] = acc
+    assert np.allclose(adv1.numpy(), ret - val, atol=1e-10) and np.allclose(vs1.numpy(), ret, atol=1e-10)
+
+
+def test_tanh_normal_log_prob_and_entropy_against_torch_distributions():
+    import torch
+    from torch.distributions import Normal, TransformedDistribution
+    from torch.distributions.transforms import TanhTransform
+    from phase_guided_terrain_traversal_b200.ppo import tanh_normal_entropy, tanh_normal_log_prob
+    torch.manual_seed(0)
+    logits = torch.randn(50, 24, dtype=torch.float64)
+    raw = torch.randn(50, 12, dtype=torch.float64)
+    loc, sr = logits.chunk(2, -1)
+    scale = torch.nn.functional.softplus(sr) + 0.001
+    d = TransformedDistribution(Normal(loc, scale), [TanhTransform(cache_size=1)])
+    ref = d.log_prob(torch.tanh(raw)).sum(-1)
+    assert torch.allclose(tanh_normal_log_prob(logits, raw), ref, atol=1e-6)
+    eps = torch.randn(50, 12, dtype=torch.float64)
+    sample = loc + scale * eps
+    ref_ent = (Normal(loc, scale).entropy() + torch.log(1 - torch.tanh(sample) ** 2)).sum(-1)
+    assert torch.allclose(tanh_normal_entropy(logits, eps), ref_ent, atol=1e-6)
+
+
+def test_ppo_loss_on_policy_properties():
+    """With behaviour == target policy the ratio is 1: the policy loss is minus the mean normalised advantage (~0) and its
+    gradient equals the REINFORCE gradient; the value loss is 0.25 * MSE against the GAE targets."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo
+    torch.manual_seed(1)
+    cfg = ppo.PPOConfig()
+    gen = torch.Generator().manual_seed(0)
+    pp = ppo.lecun_uniform_params((171, 64, 24), gen, "cpu")
+    vp = ppo.lecun_uniform_params((215, 64, 1), gen, "cpu")
+    T, B = 5, 16
+    obs, obs_priv = torch.randn(T + 1, B, 171), torch.randn(T + 1, B, 215)
+    logits = ppo.mlp(obs[:T], *pp)
+    loc, sr = logits.chunk(2, -1)
+    raw = (loc + (torch.nn.functional.softplus(sr) + 0.001) * torch.randn(T, B, 12)).detach()
+    batch = {"obs": obs, "obs_priv": obs_priv, "raw_action": raw, "log_prob": ppo.tanh_normal_log_prob(logits, raw).detach(),
+             "reward": torch.randn(T, B), "discount": torch.ones(T, B), "truncation": torch.zeros(T, B), "eps": torch.randn(T, B, 12)}
+    total, m = ppo.ppo_loss(pp, vp, batch, cfg)
+    assert abs(float(m["policy_loss"])) < 1e-5                       # mean of normalised advantages
+    base = ppo.mlp(obs_priv, *vp).squeeze(-1)
+    vs, _ = ppo.compute_gae(batch["truncation"], torch.zeros(T, B), batch["reward"], base[:T].detach(), base[T].detach(), cfg.gae_lambda, cfg.discounting)
+    assert abs(float(m["v_loss"]) - 0.25 * float(((vs - base[:T].detach()) ** 2).mean())) < 1e-6
+    assert abs(float(total) - float(m["policy_loss"] + m["v_loss"] - cfg.entropy_cost * m["entropy"])) < 1e-6
+    total.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pp[0] + vp[0])
+
+
+def test_running_stats_merge_equals_batch_statistics():
+    import torch
+    from phase_guided_terrain_traversal_b200.ppo import RunningStats
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(100, 7, generator=g) * 3 + 1, torch.randn(50, 7, generator=g) - 2, torch.randn(300, 7, generator=g) * 0.1]
+    rs = RunningStats(7, "cpu")
+    for x in xs:
+        rs.update(x)
+    full = torch.cat(xs).double()
+    assert float(rs.count) == 450 and torch.allclose(rs.mean, full.mean(0), atol=1e-10)
+    assert torch.allclose(rs.std, full.std(0, unbiased=False), atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_runs_and_is_consistent_with_the_policy_kernel(train_cfg, tmp_path, graph):
+    """Two training steps on 256 flat-terrain envs: the learner's log-prob of the stored raw actions under the
+    COLLECTION parameters matches what the tcgen05 policy kernel reported (bf16 operands vs fp32: median < 2e-2), losses are finite,
+    parameters move, and the exported pickle has the reference's layout."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import policy_io, ppo, prng
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    from phase_guided_terrain_traversal_b200.go2.randomize_simple import domain_randomize
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+    n = 256
+    cfg = ppo.PPOConfig(num_envs=n, batch_size=64, num_minibatches=8, num_updates_per_batch=2, use_cuda_graph=graph, seed=3)
+    env = Joystick(task="flat_terrain", config=train_cfg)
+    keys = prng.env_keys(1, n)
+    wenv = wrap_for_brax_training(env, episode_length=1000, randomization_fn=lambda m: domain_randomize(m, rng=keys))
+    state = wenv.reset(keys)
+    tr = ppo.PPOTrainer(wenv, state, cfg)
+    assert tr.unrolls_per_step == 2 and tr.mb == 64
+    # consistency of the two policy implementations at the collection parameters
+    _, ro = tr.collector.collect()
+    with torch.no_grad():   # (an autograd graph built on the legacy stream would pin the parameters' AccumulateGrad nodes to it,
+        #                     and the captured backward may not touch the legacy stream)
+        logits = ppo.mlp(ro.obs_state[:-1], *tr.policy_params)
+        lp = ppo.tanh_normal_log_prob(logits, ro.raw_action)
+    torch.cuda.synchronize()
+    # the kernel rounds weights and activations to bf16, the learner is fp32: ~1e-2 on a log-prob summed over 12 dims
+    # (an importance-ratio noise of 1 %, far inside the 0.3 clip)
+    d = (lp.detach() - ro.log_prob).abs()
+    assert float(d.max()) < 0.3 and float(d.median()) < 2e-2, (float(d.max()), float(d.median()))
+    before = [p.detach().clone() for p in tr.params]
+    for _ in range(2):
+        m = tr.training_step()
+        assert all(math.isfinite(v) for v in m.values()), m
+    assert any(float((a - b.detach()).abs().max()) > 0 for a, b in zip(before, tr.params))
+    assert m["env_steps"] == 2 * 2 * 20 * n                        # the extra collect above is not counted
+    tr.save(tmp_path / "policy_test")
+    d = policy_io.load_policy(tmp_path / "policy_test")
+    assert [k.shape for k in d["policy"][0]] == [(171, 512), (512, 256), (256, 128), (128, 24)]
+    assert [k.shape for k in d["value"][0]] == [(215, 512), (512, 256), (256, 128), (128, 1)]
+    assert d["count"] == 2 * 2 * 20 * n
