@@ -348,9 +348,10 @@ def main():
                         "what": "policy MLP 171-512-256-128-24 (tcgen05, bf16 operands, fp32 accumulate, random init) + wrapped env step + "
                                 "transition record into [T,N,.] buffers; back-to-back (no L2 flush)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "pgtt_env_kernel<OP_STEP>", "kernel_ms": kernel_ms,
+                         "peak_source": peak_src, "kernel": abi.step_kernel(), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_env_step": B_ALG,
-                         "note": "kernel is fp32-issue/latency bound, not HBM bound (SURVEY 8d, DESIGN.md): ~210 FLOP/B",
+                         "note": "kernel is fp32-issue/latency bound, not HBM bound (SURVEY 8d, DESIGN.md 3): ~210 FLOP/B; ncu dram traffic per "
+                                 "launch in profiles/r01c_summary.md (L2-resident state: below the algorithmic bytes)",
                          "fp32_tflops_est": FLOP_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e12},
             "clocks": sampler.summary(),
             "health": {"done_rate_last_step": done_rate, "solver_niter_mean": niter, "state_finite": finite},

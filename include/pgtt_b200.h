@@ -151,6 +151,9 @@ int pgtt_debug_forward(pgtt_env* env, float* out, void* stream);
 
 /* Counters the bench reports: kernels launched by this handle since creation. */
 int64_t pgtt_launch_count(pgtt_env* env);
+/* Which fused step kernel this handle launches: 0 = warp-per-env (pgtt_env_kernel), 1 = quad-per-env (pgtt_quad_kernel).
+ * Chosen at creation from num_envs (measured crossover) or PGTT_KERNEL=warp|quad. */
+int pgtt_step_kernel_generation(pgtt_env* env);
 
 /* ---- rollout collector: acting step of brax ppo (training/train.py:135-161,242-263; network spec as re-hosted by
  * deploy/policy_net.py:35-64). One fused tcgen05 kernel: normalise obs -> MLP (swish) -> NormalTanh sample. ---- */

@@ -190,6 +190,7 @@ def declare(lib):
     lib.pgtt_launch_count.argtypes = [vp]
     lib.pgtt_launch_count.restype = C.c_int64
     lib.pgtt_record.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.pgtt_step_kernel_generation.argtypes = [vp]
     if hasattr(lib, "pgtt_policy_create"):     # absent from the host-emulated test library (env kernels only)
         lib.pgtt_policy_last_error.restype = C.c_char_p
         lib.pgtt_policy_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
@@ -205,7 +206,7 @@ def declare(lib):
 
 ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
-    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record",
+    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act", "pgtt_store_slot",
     "pgtt_policy_launch_count", "pgtt_rollout",
 ]

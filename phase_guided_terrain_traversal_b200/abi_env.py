@@ -147,6 +147,9 @@ class AbiEnv:
     def launch_count(self) -> int:
         return int(self.lib.pgtt_launch_count(self.h))
 
+    def step_kernel(self) -> str:
+        return "pgtt_quad_kernel<OP_STEP>" if int(self.lib.pgtt_step_kernel_generation(self.h)) == 1 else "pgtt_env_kernel<OP_STEP>"
+
     # -- host-side convenience (tests) ----------------------------------------------------
     def get(self, name) -> np.ndarray:
         self.sync()

@@ -600,6 +600,7 @@ int pgtt_get_buffers(pgtt_env* e, pgtt_buffers* o) {
 }
 
 int64_t pgtt_launch_count(pgtt_env* e) { return e ? e->launches : 0; }
+int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
 
 int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* tr, void* stream) {
   if (!e) return fail(PGTT_ERR_ARG, "pgtt_record: null handle");

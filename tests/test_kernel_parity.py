@@ -248,3 +248,42 @@ def test_kernel_generations_agree_at_scale(train_cfg):
     # the two quad variants scan different box sets but must produce identical bits
     for k in outs["cuda-quad"]:
         assert np.array_equal(outs["cuda-quad"][k], outs["cuda-quadfull"][k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gen", ["warp", "quad"])
+def test_full_size_determinism_and_shard_equivalence(train_cfg, gen):
+    """BASELINE-size properties that need no oracle (4096 envs, level07 + DR, 25 wrapped steps incl. auto-resets):
+    (a) the same keys and actions give bit-identical states on a second handle; (b) two handles that each own half of the
+    envs (index sharding with key offsets, as one rank per GPU does) reproduce the single-handle run bit for bit;
+    (c) every state stays finite and some episodes end (auto-reset exercised)."""
+    n, steps = 4096, 25
+    m = gm.compile_model("stairs")
+    table = terr_mod.load_terrain("level07")
+    from phase_guided_terrain_traversal_b200 import sharding
+    keys = sharding.shard_keys(3, n, 0, 1)
+    rng = np.random.default_rng(1)
+    acts = [rng.uniform(-1, 1, (n, 12)).astype(np.float32) for _ in range(steps)]
+    fields = ("qpos", "qvel", "obs_state", "obs_privileged", "reward", "done", "rng", "last_contact", "episode_metrics", "steps")
+
+    def run(lo, hi):
+        env = make_env("cuda-" + gen if gen == "quad" else "cuda", m, train_cfg, hi - lo)
+        k = keys[lo:hi]
+        env.set_terrain(table); env.randomize(k, True); env.reset(k + np.uint32(1))
+        ndone = 0.0
+        for a in acts:
+            env.step(a[lo:hi], wrapped=True)
+            ndone += float(env.get("done").sum())
+        out = {f: env.get(f).copy() for f in fields}
+        env.close()
+        return out, ndone
+
+    full, ndone = run(0, n)
+    again, _ = run(0, n)
+    lo_half, _ = run(0, n // 2)
+    hi_half, _ = run(n // 2, n)
+    assert ndone > 0
+    for f in fields:
+        assert np.isfinite(full[f].astype(np.float64)).all(), f
+        assert np.array_equal(full[f], again[f]), ("determinism", f)
+        assert np.array_equal(full[f], np.concatenate([lo_half[f], hi_half[f]])), ("sharding", f)
