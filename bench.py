@@ -41,6 +41,14 @@ B_ALG = 3552
 FLOP_PER_ENV_STEP = 0.75e6     # SURVEY.md 8d estimate, used only for the secondary fp32 figure
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed `ncu --set full` captures
+# (profiles/r01b_step_kernel_summary.md, profiles/r01c_summary.md); only quoted for the exact configuration that was profiled
+NCU_TRAFFIC_BYTES = {
+    ("pgtt_env_kernel<OP_STEP>", "stairs", "level1", 4096, False): 5.04e6 + 0.12e6,
+    ("pgtt_quad_kernel<OP_STEP>", "stairs", "level07", 8192, True): 8.43e6 + 18.50e6,
+}
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -347,7 +355,8 @@ def main():
                         "ms_per_env_step_batch": ms_rollout / (T * n_unroll), "gpu_launches": int(rollout_launches),
                         "what": "policy MLP 171-512-256-128-24 (tcgen05, bf16 operands, fp32 accumulate, random init) + wrapped env step + "
                                 "transition record into [T,N,.] buffers; back-to-back (no L2 flush)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get((abi.step_kernel(), args.task, args.terrain, N, bool(args.dr))),
                          "peak_source": peak_src, "kernel": abi.step_kernel(), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_env_step": B_ALG,
                          "note": "kernel is fp32-issue/latency bound, not HBM bound (SURVEY 8d, DESIGN.md 3): ~210 FLOP/B; ncu dram traffic per "

@@ -47,6 +47,9 @@ class PPOConfig:                      # names and defaults of training/train.py:
     value_hidden_layer_sizes: Sequence[int] = (512, 256, 128)
     seed: int = 0
     use_cuda_graph: bool = True
+    # learner GEMM precision: "highest" = fp32 like the reference (jax_default_matmul_precision=highest, train.py:94),
+    # "high" = TF32 tensor cores (fp32 storage and accumulation, 10-bit mantissa products)
+    matmul_precision: str = "highest"
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -175,6 +178,9 @@ class PPOTrainer:
         import torch
         import torch.distributed as dist
         self.torch, self.cfg, self.wenv, self.group = torch, cfg, wenv, group
+        if cfg.matmul_precision not in ("highest", "high"):
+            raise ValueError("matmul_precision must be 'highest' or 'high'")
+        torch.set_float32_matmul_precision(cfg.matmul_precision)
         self.env = wenv.unwrapped
         self.abi = self.env._abi
         self.dev = self.abi.torch_device
