@@ -38,7 +38,7 @@ extern "C" {
 #define PGTT_NU 12
 #define PGTT_NBOX 100
 #define PGTT_NRAY 117          /* 13 x 9 */
-#define PGTT_NOBS 171
+#define PGTT_NOBS 171          /* phase-guided task; the baseline variant has 162 / 206 (pgtt_obs_dims) */
 #define PGTT_NPRIV 215
 #define PGTT_NMETRIC 22        /* 21 reward terms (order of go2/configs.py:31-59) + swing_peak */
 #define PGTT_NSENSOR 49
@@ -85,6 +85,7 @@ typedef struct {
   double default_pose[12], home_qpos[19];
   int history_update_steps, episode_length, n_substeps;
   int rng_partitionable;       /* jax_threefry_partitionable: 1 = JAX >= 0.5 default */
+  int variant;                 /* 0 = go2/joystick_pgtt.py (obs 171 / 215), 1 = go2/joystick.py baseline task (obs 162 / 206) */
 } pgtt_task_desc;
 
 /* Device pointers into the handle's state, [num_envs][dim] row-major. float unless noted. */
@@ -143,6 +144,8 @@ int pgtt_forward(pgtt_env* env, void* stream);
 int pgtt_heightscan(pgtt_env* env, const float* center, const float* yaw, float* out, void* stream);
 
 int pgtt_get_buffers(pgtt_env* env, pgtt_buffers* out);
+/* Row lengths of obs_state / obs_privileged for this handle's task variant (171 / 215 or 162 / 206). */
+int pgtt_obs_dims(pgtt_env* env, int* nobs, int* npriv);
 
 /* Debug / parity probe: one mjx.forward with every intermediate written to `out`
  * (DEVICE float [num_envs][PGTT_DEBUG_FLOATS]); layout in csrc/pgtt_debug.h. */

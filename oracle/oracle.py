@@ -99,7 +99,7 @@ def pack_model(m, n_model_bodies: int | None = None) -> np.ndarray:
     return np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in parts])
 
 
-def pack_task(cfg, m, rng_partitionable: bool = True) -> np.ndarray:
+def pack_task(cfg, m, rng_partitionable: bool = True, variant: int = 0) -> np.ndarray:
     """Flatten the task config (`go2.configs.default_config()` layout) for `orc_create`."""
     n = cfg.noise_config
     r = cfg.reward_config
@@ -109,7 +109,7 @@ def pack_task(cfg, m, rng_partitionable: bool = True) -> np.ndarray:
         [r.scales[k] for k in REWARD_KEYS], [r.tracking_sigma, r.swing_height, r.base_feet_distance, r.phase_sigma],
         cfg.command_config.u_max, cfg.command_config.u_min, cfg.command_config.b, cfg.gait_freq,
         [cfg.soft_joint_pos_limit_factor], m.home_qpos[7:], m.home_qpos,
-        [cfg.history_update_steps, cfg.episode_length, int(round(cfg.ctrl_dt / cfg.sim_dt)), int(rng_partitionable)],
+        [cfg.history_update_steps, cfg.episode_length, int(round(cfg.ctrl_dt / cfg.sim_dt)), int(rng_partitionable), int(variant)],
     ]
     return np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in parts])
 
@@ -117,12 +117,13 @@ def pack_task(cfg, m, rng_partitionable: bool = True) -> np.ndarray:
 class Oracle:
     """N independent CPU envs. All I/O as float64 / int numpy arrays with leading N."""
 
-    def __init__(self, model, cfg, n_envs: int, precision: str = "f32", rng_partitionable: bool = True):
+    def __init__(self, model, cfg, n_envs: int, precision: str = "f32", rng_partitionable: bool = True, variant: int = 0):
         self.lib = _lib(precision)
         self.n = n_envs
         self.model, self.cfg = model, cfg
         mc = pack_model(model)
-        tc = pack_task(cfg, model, rng_partitionable)
+        tc = pack_task(cfg, model, rng_partitionable, variant)
+        self.variant = int(variant)
         self.h = self.lib.orc_create(n_envs, mc.ctypes.data, mc.size, tc.ctypes.data, tc.size)
         if not self.h:
             raise RuntimeError("orc_create failed")

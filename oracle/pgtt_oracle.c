@@ -909,30 +909,35 @@ static void get_obs(const TaskCfg* t, Env* e) { /* joystick_pgtt.py:238-370 */
   split2(part, in->rng, key);
   for (int i = 0; i < 12; i++) o[18 + i] = d->qvel[6 + i] + (2 * rng_uniform(part, key, 12, i, 0, 1) - 1) * lvl * t->noise_joint_vel;
   split2(part, in->rng, key); /* linvel noise key, re-used for the heightscan */
-  for (int i = 0; i < 4; i++) { o[30 + i] = COS(in->phase[i]); o[34 + i] = SIN(in->phase[i]); }
+  /* baseline task (go2/joystick.py:333-341): no phase block, no gait_freq -> 162 / 206 entries */
+  const int bv = t->variant != 0, o_scan = bv ? 30 : 38, o_last = bv ? 147 : 156, o_cmd = bv ? 159 : 168, nobs = bv ? NOBS - 9 : NOBS;
+  if (!bv) for (int i = 0; i < 4; i++) { o[30 + i] = COS(in->phase[i]); o[34 + i] = SIN(in->phase[i]); }
   real zmin = INFINITY;
   for (int i = 0; i < NRAY; i++) if (in->heightscan[i][2] < zmin) zmin = in->heightscan[i][2];
   for (int i = 0; i < NRAY; i++)
-    o[38 + i] = (in->heightscan[i][2] - zmin) + (2 * rng_uniform(part, key, NRAY, i, 0, 1) - 1) * lvl * t->noise_heightscan;
+    o[o_scan + i] = (in->heightscan[i][2] - zmin) + (2 * rng_uniform(part, key, NRAY, i, 0, 1) - 1) * lvl * t->noise_heightscan;
   if (in->step % t->history_update_steps == 0) {
     memmove(in->qvel_history + 12, in->qvel_history, sizeof(real) * 12);
     memmove(in->qpos_error_history + 12, in->qpos_error_history, sizeof(real) * 12);
     for (int i = 0; i < 12; i++) { in->qvel_history[i] = d->qvel[6 + i]; in->qpos_error_history[i] = d->qpos[7 + i] - in->motor_targets[i]; }
   }
-  o[155] = in->gait_freq;
-  for (int i = 0; i < 12; i++) o[156 + i] = in->last_act[i];
-  for (int i = 0; i < 3; i++) o[168 + i] = in->command[i];
+  if (!bv) o[155] = in->gait_freq;
+  for (int i = 0; i < 12; i++) o[o_last + i] = in->last_act[i];
+  for (int i = 0; i < 3; i++) o[o_cmd + i] = in->command[i];
+  for (int i = nobs; i < NOBS; i++) o[i] = 0;
   real* p = e->obs_priv;
-  memcpy(p, o, sizeof(real) * NOBS);
-  for (int i = 0; i < 3; i++) { p[171 + i] = d->sensordata[19 + i]; p[174 + i] = d->sensordata[3 + i]; p[177 + i] = d->sensordata[16 + i]; }
-  for (int i = 0; i < 12; i++) p[180 + i] = d->actuator_force[i];
-  for (int i = 0; i < 4; i++) p[192 + i] = (real)in->last_contact[i];
-  for (int i = 0; i < 12; i++) p[196 + i] = d->sensordata[37 + i];
-  for (int i = 0; i < 4; i++) p[208 + i] = in->feet_air_time[i];
-  p[212] = p[213] = p[214] = 0; /* xfrc_applied[torso,:3] is never written in this fork */
+  memcpy(p, o, sizeof(real) * nobs);
+  real* x = p + nobs;
+  for (int i = 0; i < 3; i++) { x[i] = d->sensordata[19 + i]; x[3 + i] = d->sensordata[3 + i]; x[6 + i] = d->sensordata[16 + i]; }
+  for (int i = 0; i < 12; i++) x[9 + i] = d->actuator_force[i];
+  for (int i = 0; i < 4; i++) x[21 + i] = (real)in->last_contact[i];
+  for (int i = 0; i < 12; i++) x[25 + i] = d->sensordata[37 + i];
+  for (int i = 0; i < 4; i++) x[37 + i] = in->feet_air_time[i];
+  x[41] = x[42] = x[43] = 0; /* xfrc_applied[torso,:3] is never written in this fork */
+  for (int i = nobs + 44; i < NPRIV; i++) p[i] = 0;
 }
 
-static void quadrant_stats(Info* in) { /* joystick_pgtt.py:169-190, n = 6 for both axes */
+static void quadrant_stats(const TaskCfg* t, Info* in) { /* joystick_pgtt.py:169-190, n = 6 for both axes */
   const int n = (NRAY_H - 1) / 2;
   const int r0[4] = {0, 0, n + 1, n + 1}, r1[4] = {n, n, NRAY_H, NRAY_H};
   const int c0[4] = {n + 1, 0, n + 1, 0}, c1[4] = {NRAY_W, n, NRAY_W, n};
@@ -940,7 +945,7 @@ static void quadrant_stats(Info* in) { /* joystick_pgtt.py:169-190, n = 6 for bo
     real mx = -INFINITY, mn = INFINITY;
     for (int i = r0[q]; i < r1[q]; i++)
       for (int j = c0[q]; j < c1[q]; j++) { real z = in->heightscan[i * NRAY_W + j][2]; if (z > mx) mx = z; if (z < mn) mn = z; }
-    in->H_max[q] = mx - mn; in->H_min[q] = mn;
+    in->H_max[q] = t->variant ? mx : mx - mn; in->H_min[q] = mn; /* joystick.py:186 vs joystick_pgtt.py:189 */
   }
 }
 
@@ -1008,7 +1013,7 @@ void orc_task_step(const TaskCfg* t, Env* e, const real* action) {
   real pfz[4];
   for (int i = 0; i < 4; i++) { pfz[i] = s[25 + 3 * i + 2]; if (pfz[i] > in->swing_peak[i]) in->swing_peak[i] = pfz[i]; }
   orc_heightscan(m, d->qpos, quat_to_yaw(d->qpos + 3), in->heightscan);
-  quadrant_stats(in);
+  quadrant_stats(t, in);
   get_obs(t, e);
   int done = s[24] < 0; /* upvector z */
   /* rewards, in the dict order of _get_reward (joystick_pgtt.py:382-420) */
@@ -1049,12 +1054,13 @@ void orc_task_step(const TaskCfg* t, Env* e, const real* action) {
     const real* v = s + 37 + 3 * i; const real* pf = s + 25 + 3 * i;
     real vxy2 = v[0] * v[0] + v[1] * v[1];
     slip += vxy2 * contact[i];
-    clear += FABS(pf[2] - (in->H_max[i] + t->swing_height)) * SQRT(SQRT(vxy2));
+    if (t->variant) clear += FABS(d->foot_xpos[foot_of_sensor[i]][2] - (in->H_max[i] - t->base_feet_distance + t->swing_height)) * SQRT(SQRT(vxy2)); /* joystick.py:569-572 */
+    else clear += FABS(pf[2] - (in->H_max[i] + t->swing_height)) * SQRT(SQRT(vxy2));
     real rz = gait_get_z(in->phase[i], in->H_max[i] + t->swing_height, t->base_feet_distance);
     phase_err += (pf[2] - rz) * (pf[2] - rz);
     int swing_mask = (in->phase[i] / (2 * PI_R)) >= (real)0.5;
     swing += (pf[2] - t->swing_height) * (pf[2] - t->swing_height) * swing_mask;
-    air += (in->feet_air_time[i] - (real)0.1) * first_contact[i];
+    air += (in->feet_air_time[i] - (t->variant ? (real)0.5 : (real)0.1)) * first_contact[i]; /* joystick.py:591 vs joystick_pgtt.py:597 */
     con += (real)(swing_mask && contact[i]);
     center += pf[0] * pf[0] + pf[1] * pf[1]; /* init_feet_pos stays zero (joystick_pgtt.py:130 is a no-op) */
     real er = in->swing_peak[i] / t->swing_height - 1;
@@ -1230,7 +1236,7 @@ void* orc_create(int n_envs, const double* mc, int n_mc, const double* tc, int n
   TAKE(t->reward_scale, NREW); TAKE(&t->tracking_sigma, 1); TAKE(&t->swing_height, 1); TAKE(&t->base_feet_distance, 1); TAKE(&t->phase_sigma, 1);
   TAKE(t->cmd_u_max, 3); TAKE(t->cmd_u_min, 3); TAKE(t->cmd_b, 3); TAKE(t->gait_freq, 2); TAKE(&t->soft_limit_factor, 1);
   TAKE(t->default_pose, NHINGE); TAKE(t->home_qpos, NQ);
-  TAKEI(&t->history_update_steps, 1); TAKEI(&t->episode_length, 1); TAKEI(&t->n_substeps, 1); TAKEI(&t->rng_partitionable, 1);
+  TAKEI(&t->history_update_steps, 1); TAKEI(&t->episode_length, 1); TAKEI(&t->n_substeps, 1); TAKEI(&t->rng_partitionable, 1); TAKEI(&t->variant, 1);
   if ((int)(p - tc) != n_tc) { fprintf(stderr, "orc_create: task constant count mismatch %d vs %d\n", (int)(p - tc), n_tc); free(h->env); free(h); return NULL; }
   for (int i = 0; i < n_envs; i++) { h->env[i].m = *m; h->env[i].terrain_index = -1; }
   return h;

@@ -99,6 +99,7 @@ typedef struct {
   real soft_limit_factor;
   real default_pose[NHINGE], home_qpos[NQ];
   int history_update_steps, episode_length, n_substeps, rng_partitionable;
+  int variant; /* 0 = go2/joystick_pgtt.py, 1 = go2/joystick.py (baseline task: obs 162 / 206, first entries of the arrays) */
 } TaskCfg;
 
 typedef struct {

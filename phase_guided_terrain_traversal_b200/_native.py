@@ -69,7 +69,7 @@ class TaskDesc(C.Structure):
         ("cmd_u_max", d * 3), ("cmd_u_min", d * 3), ("cmd_b", d * 3), ("gait_freq", d * 2),
         ("soft_limit_factor", d),
         ("default_pose", d * 12), ("home_qpos", d * 19),
-        ("history_update_steps", i32), ("episode_length", i32), ("n_substeps", i32), ("rng_partitionable", i32),
+        ("history_update_steps", i32), ("episode_length", i32), ("n_substeps", i32), ("rng_partitionable", i32), ("variant", i32),
     ]
 
 
@@ -151,7 +151,7 @@ def model_desc(m) -> ModelDesc:
     return md
 
 
-def task_desc(cfg, m, rng_partitionable: bool = True) -> TaskDesc:
+def task_desc(cfg, m, rng_partitionable: bool = True, variant: int = 0) -> TaskDesc:
     td = TaskDesc()
     n, r = cfg.noise_config, cfg.reward_config
     td.ctrl_dt, td.action_scale, td.noise_level = cfg.ctrl_dt, cfg.action_scale, n.level
@@ -166,6 +166,7 @@ def task_desc(cfg, m, rng_partitionable: bool = True) -> TaskDesc:
     td.history_update_steps, td.episode_length = cfg.history_update_steps, cfg.episode_length
     td.n_substeps = int(round(cfg.ctrl_dt / cfg.sim_dt))
     td.rng_partitionable = int(rng_partitionable)
+    td.variant = int(variant)
     return td
 
 
@@ -186,6 +187,7 @@ def declare(lib):
     lib.pgtt_forward.argtypes = [vp, vp]
     lib.pgtt_heightscan.argtypes = [vp, vp, vp, vp, vp]
     lib.pgtt_get_buffers.argtypes = [vp, C.POINTER(Buffers)]
+    lib.pgtt_obs_dims.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pgtt_debug_forward.argtypes = [vp, vp, vp]
     lib.pgtt_launch_count.argtypes = [vp]
     lib.pgtt_launch_count.restype = C.c_int64
@@ -206,7 +208,7 @@ def declare(lib):
 
 ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
-    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
+    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act", "pgtt_store_slot",
     "pgtt_policy_launch_count", "pgtt_rollout",
 ]

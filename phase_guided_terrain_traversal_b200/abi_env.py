@@ -25,14 +25,16 @@ _TYPESTR = {"f": "<f4", "i": "<i4", "u": "<u4"}
 
 
 class AbiEnv:
-    def __init__(self, model, cfg, num_envs: int, device: int = 0, backend: str = "torch", lib=None, rng_partitionable: bool = True):
+    def __init__(self, model, cfg, num_envs: int, device: int = 0, backend: str = "torch", lib=None, rng_partitionable: bool = True,
+                 variant: int = 0):
         self.lib = lib if lib is not None else nat.load_library()
         self.backend = backend
         self.N = int(num_envs)
         self.device = device
         self.model, self.cfg = model, cfg
         self._md = nat.model_desc(model)
-        self._td = nat.task_desc(cfg, model, rng_partitionable)
+        self._td = nat.task_desc(cfg, model, rng_partitionable, variant)
+        self.variant = int(variant)
         h = C.c_void_p()
         nat.check(self.lib, self.lib.pgtt_create(C.byref(self._md), C.byref(self._td), device, self.N, C.byref(h)))
         self.h = h
@@ -44,7 +46,12 @@ class AbiEnv:
         b = nat.Buffers()
         nat.check(self.lib, self.lib.pgtt_get_buffers(self.h, C.byref(b)))
         self.buf = {}
+        no, npv = C.c_int(), C.c_int()
+        nat.check(self.lib, self.lib.pgtt_obs_dims(self.h, C.byref(no), C.byref(npv)))
+        self.nobs, self.npriv = no.value, npv.value
+        obs_dim = {"obs_state": self.nobs, "obs_privileged": self.npriv, "first_obs_state": self.nobs, "first_obs_privileged": self.npriv}
         for name, kind, dim in nat.BUFFER_FIELDS:
+            dim = obs_dim.get(name, dim)
             ptr = C.cast(getattr(b, name), C.c_void_p).value
             self.buf[name] = self._wrap(ptr, kind, (self.N, dim))
         self.n_terrains = 0

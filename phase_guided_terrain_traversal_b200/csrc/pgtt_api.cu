@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(32 * QWARPS_MAX) pgtt_quad_kernel(LaunchArgs a
 // transition write-out: one HBM-bound launch per control step (obs 171 + 215 floats, 3 scalars per env)
 __global__ void pgtt_record_kernel(EnvBuffers B, float* __restrict__ os, float* __restrict__ op, float* __restrict__ rw, float* __restrict__ dc,
                                    float* __restrict__ tr) {
-  const size_t n_os = (size_t)B.N * NOBS, n_op = (size_t)B.N * NPRIV, stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n_os = (size_t)B.N * GC.nobs, n_op = (size_t)B.N * GC.npriv, stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_op; i += stride) {
     if (op) op[i] = B.obs_priv[i];
     if (os && i < n_os) os[i] = B.obs_state[i];
@@ -414,6 +414,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   c.gait_freq[0] = (float)t->gait_freq[0]; c.gait_freq[1] = (float)t->gait_freq[1];
   for (int i = 0; i < NQ; i++) c.home_qpos[i] = (float)t->home_qpos[i];
   c.history_update_steps = t->history_update_steps; c.episode_length = t->episode_length; c.rng_partitionable = t->rng_partitionable;
+  c.variant = t->variant ? 1 : 0; c.nobs = c.variant ? NOBS - 9 : NOBS; c.npriv = c.nobs + 44;
   // the kernels assume the GO2 tree: x-axis abduction, y-axis hip/knee, identity body quats (checked by the Python model compiler)
 
   EnvBuffers& B = e->B;
@@ -600,13 +601,20 @@ int pgtt_get_buffers(pgtt_env* e, pgtt_buffers* o) {
 }
 
 int64_t pgtt_launch_count(pgtt_env* e) { return e ? e->launches : 0; }
+int pgtt_obs_dims(pgtt_env* e, int* nobs, int* npriv) {
+  if (!e) return fail(PGTT_ERR_ARG, "pgtt_obs_dims: null handle");
+  if (nobs) *nobs = e->mc.nobs;
+  if (npriv) *npriv = e->mc.npriv;
+  return PGTT_OK;
+}
 int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
 
 int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* tr, void* stream) {
   if (!e) return fail(PGTT_ERR_ARG, "pgtt_record: null handle");
+  if (int rc = upload_consts(e)) return rc;
   const EnvBuffers& B = e->B;
 #ifndef PGTT_HOST_EMU
-  const size_t n = (size_t)B.N * NPRIV;
+  const size_t n = (size_t)B.N * e->mc.npriv;
   const int threads = 256;
   size_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -615,8 +623,8 @@ int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* 
 #else
   (void)stream;
   const size_t N = (size_t)B.N;
-  if (os) memcpy(os, B.obs_state, N * NOBS * sizeof(float));
-  if (op) memcpy(op, B.obs_priv, N * NPRIV * sizeof(float));
+  if (os) memcpy(os, B.obs_state, N * e->mc.nobs * sizeof(float));
+  if (op) memcpy(op, B.obs_priv, N * e->mc.npriv * sizeof(float));
   for (size_t i = 0; i < N; i++) {
     if (rw) rw[i] = B.reward[i];
     if (dc) dc[i] = 1.0f - B.done[i];

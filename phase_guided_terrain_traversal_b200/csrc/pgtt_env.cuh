@@ -147,10 +147,13 @@ DEV void write_obs(WS& w, const EnvBuffers& B, int env, Key& rng, const float* p
   Key chain[5];
 #pragma unroll
   for (int s = 0; s < 5; s++) { chain[s] = rng; rng = rng_split(rng, 2, 0); }
-  float* o = B.obs_state + (size_t)env * NOBS;
-  float* pr = B.obs_priv + (size_t)env * NPRIV;
+  float* o = B.obs_state + (size_t)env * GC.nobs;
+  float* pr = B.obs_priv + (size_t)env * GC.npriv;
   const float lvl = GC.noise_level;
   const float* R = w.xmat[0];
+  // layout: the baseline variant (go2/joystick.py:333-341) has no phase block and no gait_freq
+  const bool base_v = GC.variant != 0;
+  const int o_scan = base_v ? 30 : 38, o_last = base_v ? 147 : 156, o_cmd = base_v ? 159 : 168, px = GC.nobs;
   {
     // slot group of this lane: gyro 0..2 | gravity 3..5 | joint pos 6..17 | joint vel 18..29
     const int grp = lane < 3 ? 0 : (lane < 6 ? 1 : (lane < 18 ? 2 : 3));
@@ -169,7 +172,7 @@ DEV void write_obs(WS& w, const EnvBuffers& B, int env, Key& rng, const float* p
     if (lane < 30) { o[lane] = v; pr[lane] = v; }
   }
   const Key scan_key = rng_split(chain[4], 2, 1);   // the linvel key, re-used for the height scan (Q9)
-  if (lane < 4) {
+  if (lane < 4 && !base_v) {
     float s, c;
     sincos_(phase[lane], &s, &c);
     o[30 + lane] = c; o[34 + lane] = s; pr[30 + lane] = c; pr[34 + lane] = s;
@@ -179,17 +182,17 @@ DEV void write_obs(WS& w, const EnvBuffers& B, int env, Key& rng, const float* p
   zmin = warp_min(zmin);
   for (int r = lane; r < NRAY; r += 32) {
     const float z = (w.scan[r] - zmin) + (2.f * rng_unit(scan_key, NRAY, r) - 1.f) * lvl * GC.noise_heightscan;
-    o[38 + r] = z; pr[38 + r] = z;
+    o[o_scan + r] = z; pr[o_scan + r] = z;
   }
-  if (lane == 0) { o[155] = gait_freq; pr[155] = gait_freq; }
-  if (lane < 12) { o[156 + lane] = last_act[lane]; pr[156 + lane] = last_act[lane]; }
+  if (lane == 0 && !base_v) { o[155] = gait_freq; pr[155] = gait_freq; }
+  if (lane < 12) { o[o_last + lane] = last_act[lane]; pr[o_last + lane] = last_act[lane]; }
   if (lane < 3) {
-    o[168 + lane] = command[lane]; pr[168 + lane] = command[lane];
-    pr[171 + lane] = w.sens[19 + lane]; pr[174 + lane] = w.sens[3 + lane]; pr[177 + lane] = w.sens[16 + lane];
-    pr[212 + lane] = 0.f;
+    o[o_cmd + lane] = command[lane]; pr[o_cmd + lane] = command[lane];
+    pr[px + lane] = w.sens[19 + lane]; pr[px + 3 + lane] = w.sens[3 + lane]; pr[px + 6 + lane] = w.sens[16 + lane];
+    pr[px + 41 + lane] = 0.f;
   }
-  if (lane < 12) { pr[180 + lane] = w.actf[lane]; pr[196 + lane] = w.sens[37 + lane]; }
-  if (lane < 4) { pr[192 + lane] = (float)last_contact[lane]; pr[208 + lane] = feet_air_time[lane]; }
+  if (lane < 12) { pr[px + 9 + lane] = w.actf[lane]; pr[px + 25 + lane] = w.sens[37 + lane]; }
+  if (lane < 4) { pr[px + 21 + lane] = (float)last_contact[lane]; pr[px + 37 + lane] = feet_air_time[lane]; }
 }
 
 // history rolls of _get_obs (joystick_pgtt.py:319-334), `step` is info["step"] BEFORE the increment
@@ -274,7 +277,7 @@ DEV void env_step(WS& w, const EnvBuffers& B, const float* action_all, int env, 
       mx = fmaxf(mx, z); mn = fminf(mn, z);
     }
     for (int o = 4; o > 0; o >>= 1) { mx = fmaxf(mx, shfl_xor(mx, o)); mn = fminf(mn, shfl_xor(mn, o)); }
-    const float hm = mx - mn;
+    const float hm = GC.variant ? mx : mx - mn;   // joystick.py:186 vs joystick_pgtt.py:189
     // lane k (< 4) needs quadrant k
     hmax = shfl(hm, (lane & 3) * 8);
     const float hmin = shfl(mn, (lane & 3) * 8);
@@ -321,12 +324,13 @@ DEV void env_step(WS& w, const EnvBuffers& B, const float* action_all, int env, 
     const float* v = sdat + 37 + 3 * lane; const float* pf = sdat + 25 + 3 * lane;
     const float vxy2 = v[0] * v[0] + v[1] * v[1];
     slip = vxy2 * (float)contact;
-    clr = fabsf(pf[2] - (hmax + GC.swing_height)) * sqrtf(sqrtf(vxy2));
+    clr = (GC.variant ? fabsf(w.foot[lane ^ 1][2] - (hmax - GC.base_feet_distance + GC.swing_height))   // world-frame foot height, joystick.py:569-572
+                      : fabsf(pf[2] - (hmax + GC.swing_height))) * sqrtf(sqrtf(vxy2));
     const float rz = gait_get_z(phase, hmax + GC.swing_height, GC.base_feet_distance);
     perr = (pf[2] - rz) * (pf[2] - rz);
     const int swing_mask = (phase / (2.f * PGTT_PI)) >= 0.5f;
     swing = (pf[2] - GC.swing_height) * (pf[2] - GC.swing_height) * (float)swing_mask;
-    airr = (air - 0.1f) * (float)first_contact;
+    airr = (air - (GC.variant ? 0.5f : 0.1f)) * (float)first_contact;   // joystick.py:591 vs joystick_pgtt.py:597
     con = (float)(swing_mask && contact);
     center = pf[0] * pf[0] + pf[1] * pf[1];
     const float er = swing_peak / GC.swing_height - 1.f;
@@ -448,8 +452,8 @@ DEV void env_step(WS& w, const EnvBuffers& B, const float* action_all, int env, 
       if (lane < 9) B.site_xmat[env * 9 + lane] = B.first_site_xmat[env * 9 + lane];
       if (lane < NCON) B.contact_dist[env * NCON + lane] = B.first_contact_dist[env * NCON + lane];
       if (lane < 2 * NCON) B.contact_geom[env * NCON * 2 + lane] = B.first_contact_geom[env * NCON * 2 + lane];
-      for (int i = lane; i < NOBS; i += 32) B.obs_state[(size_t)env * NOBS + i] = B.first_obs_state[(size_t)env * NOBS + i];
-      for (int i = lane; i < NPRIV; i += 32) B.obs_priv[(size_t)env * NPRIV + i] = B.first_obs_priv[(size_t)env * NPRIV + i];
+      for (int i = lane; i < GC.nobs; i += 32) B.obs_state[(size_t)env * GC.nobs + i] = B.first_obs_state[(size_t)env * GC.nobs + i];
+      for (int i = lane; i < GC.npriv; i += 32) B.obs_priv[(size_t)env * GC.npriv + i] = B.first_obs_priv[(size_t)env * GC.npriv + i];
       if (lane == 0) B.time[env] = 0.f;
     }
   }
@@ -537,8 +541,8 @@ DEV void env_reset(WS& w, const EnvBuffers& B, const uint32_t* keys, int env, in
   if (lane < 9) B.first_site_xmat[env * 9 + lane] = w.xmat[0][lane];
   if (lane < NCON) B.first_contact_dist[env * NCON + lane] = B.contact_dist[env * NCON + lane];
   if (lane < 2 * NCON) B.first_contact_geom[env * NCON * 2 + lane] = B.contact_geom[env * NCON * 2 + lane];
-  for (int i = lane; i < NOBS; i += 32) B.first_obs_state[(size_t)env * NOBS + i] = B.obs_state[(size_t)env * NOBS + i];
-  for (int i = lane; i < NPRIV; i += 32) B.first_obs_priv[(size_t)env * NPRIV + i] = B.obs_priv[(size_t)env * NPRIV + i];
+  for (int i = lane; i < GC.nobs; i += 32) B.first_obs_state[(size_t)env * GC.nobs + i] = B.obs_state[(size_t)env * GC.nobs + i];
+  for (int i = lane; i < GC.npriv; i += 32) B.first_obs_priv[(size_t)env * GC.npriv + i] = B.obs_priv[(size_t)env * GC.npriv + i];
 }
 
 // ----------------------------------------------------------------------------------------------

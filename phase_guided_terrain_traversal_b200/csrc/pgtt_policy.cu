@@ -496,17 +496,19 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t
   pgtt_buffers b;
   if (int rc = pgtt_get_buffers(env, &b)) return pfail(rc, pgtt_last_error());
   const size_t N = (size_t)b.num_envs, A = (size_t)pol->P.act_dim;
-  if (pol->P.obs_dim != PGTT_NOBS || A != PGTT_NU) return pfail(PGTT_ERR_ARG, "pgtt_rollout: policy must map obs[171] -> 2 x 12 logits");
+  int nobs = 0, npriv = 0;
+  pgtt_obs_dims(env, &nobs, &npriv);
+  if (pol->P.obs_dim != nobs || A != PGTT_NU) return pfail(PGTT_ERR_ARG, "pgtt_rollout: policy must map the env's obs[\"state\"] (171 or 162) -> 2 x 12 logits");
   // slot 0: the observation the unroll starts from; reward / discount / truncation slots are only written after a step
   if (int rc = pgtt_record(env, o->obs_state, o->obs_privileged, nullptr, nullptr, nullptr, stream)) return pfail(rc, pgtt_last_error());
   for (int t = 0; t < T; t++) {
     float* act = o->action + (size_t)t * N * A;
-    if (int rc = pgtt_policy_act(pol, o->obs_state + (size_t)t * N * PGTT_NOBS, (int)N, seed, step0 + (uint64_t)t, deterministic, nullptr, act,
+    if (int rc = pgtt_policy_act(pol, o->obs_state + (size_t)t * N * nobs, (int)N, seed, step0 + (uint64_t)t, deterministic, nullptr, act,
                                  o->raw_action ? o->raw_action + (size_t)t * N * A : nullptr, o->log_prob ? o->log_prob + (size_t)t * N : nullptr,
                                  nullptr, stream)) return rc;
     if (int rc = pgtt_step(env, act, 1, stream)) return pfail(rc, pgtt_last_error());
-    if (int rc = pgtt_record(env, o->obs_state + (size_t)(t + 1) * N * PGTT_NOBS,
-                             o->obs_privileged ? o->obs_privileged + (size_t)(t + 1) * N * PGTT_NPRIV : nullptr,
+    if (int rc = pgtt_record(env, o->obs_state + (size_t)(t + 1) * N * nobs,
+                             o->obs_privileged ? o->obs_privileged + (size_t)(t + 1) * N * npriv : nullptr,
                              o->reward ? o->reward + (size_t)t * N : nullptr, o->discount ? o->discount + (size_t)t * N : nullptr,
                              o->truncation ? o->truncation + (size_t)t * N : nullptr, stream)) return pfail(rc, pgtt_last_error());
   }

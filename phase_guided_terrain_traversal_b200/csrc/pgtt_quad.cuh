@@ -1320,10 +1320,13 @@ DEV void q_write_obs(const EnvBuffers& B, QShared& Sh, int env, int slot, int g,
   Key chain[5];
 #pragma unroll
   for (int s = 0; s < 5; s++) { chain[s] = rng; rng = rng_split(rng, 2, 0); }
-  float* o = B.obs_state + (size_t)env * NOBS;
-  float* pr = B.obs_priv + (size_t)env * NPRIV;
+  float* o = B.obs_state + (size_t)env * GC.nobs;
+  float* pr = B.obs_priv + (size_t)env * GC.npriv;
   const float lvl = GC.noise_level;
   const int kf = g ^ 1;
+  // layout: the baseline variant (go2/joystick.py:333-341) has no phase block and no gait_freq
+  const bool base_v = GC.variant != 0;
+  const int o_scan = base_v ? 30 : 38, o_last = base_v ? 147 : 156, o_cmd = base_v ? 159 : 168, px = GC.nobs;
   {
     const Key kgyro = rng_split(chain[0], 2, 1), kgrav = rng_split(chain[1], 2, 1), kpos = rng_split(chain[2], 2, 1), kvel = rng_split(chain[3], 2, 1);
     if (g < 3 && ok) {
@@ -1346,32 +1349,32 @@ DEV void q_write_obs(const EnvBuffers& B, QShared& Sh, int env, int slot, int g,
   {
     float s, c;
     sincos_(phase_k, &s, &c);
-    if (ok) { o[30 + kf] = c; o[34 + kf] = s; pr[30 + kf] = c; pr[34 + kf] = s; }
+    if (ok && !base_v) { o[30 + kf] = c; o[34 + kf] = s; pr[30 + kf] = c; pr[34 + kf] = s; }
   }
   float zmin = Q_INF;
   for (int r = g; r < NRAY; r += 4) zmin = fminf(zmin, Sh.scan[slot][r]);
   zmin = qmin(zmin);
   for (int r = g; r < NRAY; r += 4) {
     const float z = (Sh.scan[slot][r] - zmin) + (2.f * rng_unit(scan_key, NRAY, r) - 1.f) * lvl * GC.noise_heightscan;
-    if (ok) { o[38 + r] = z; pr[38 + r] = z; }
+    if (ok) { o[o_scan + r] = z; pr[o_scan + r] = z; }
   }
   if (!ok) return;
-  if (g == 0) { o[155] = gait_freq; pr[155] = gait_freq; }
+  if (g == 0 && !base_v) { o[155] = gait_freq; pr[155] = gait_freq; }
 #pragma unroll
   for (int t = 0; t < 3; t++) {
     const int idx = 3 * g + t;
-    o[156 + idx] = last_act3[t]; pr[156 + idx] = last_act3[t];
-    pr[180 + L.act[t]] = actf[t];
-    pr[196 + 3 * kf + t] = Z.fvel[t];
+    o[o_last + idx] = last_act3[t]; pr[o_last + idx] = last_act3[t];
+    pr[px + 9 + L.act[t]] = actf[t];
+    pr[px + 25 + 3 * kf + t] = Z.fvel[t];
   }
   if (g < 3) {
-    o[168 + g] = command_g; pr[168 + g] = command_g;
+    o[o_cmd + g] = command_g; pr[o_cmd + g] = command_g;
     const float ll = g == 0 ? Z.llin[0] : (g == 1 ? Z.llin[1] : Z.llin[2]);
     const float ac = g == 0 ? Z.acc[0] : (g == 1 ? Z.acc[1] : Z.acc[2]);
     const float ga = g == 0 ? Z.gang[0] : (g == 1 ? Z.gang[1] : Z.gang[2]);
-    pr[171 + g] = ll; pr[174 + g] = ac; pr[177 + g] = ga; pr[212 + g] = 0.f;
+    pr[px + g] = ll; pr[px + 3 + g] = ac; pr[px + 6 + g] = ga; pr[px + 41 + g] = 0.f;
   }
-  pr[192 + kf] = (float)last_contact_k; pr[208 + kf] = air_k;
+  pr[px + 21 + kf] = (float)last_contact_k; pr[px + 37 + kf] = air_k;
 }
 
 // store the mjx.Data fields the task / API exposes
@@ -1484,7 +1487,7 @@ DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, i
     float mx = -Q_INF, mn = Q_INF;
     for (int r = r0; r < r1; r++)
       for (int c = c0; c < c1; c++) { const float z = Sh.scan[slot][r * NRAY_W + c]; mx = fmaxf(mx, z); mn = fminf(mn, z); }
-    hmax = mx - mn;
+    hmax = GC.variant ? mx : mx - mn;   // joystick.py:186 vs joystick_pgtt.py:189
     if (ok) { B.H_max[env * 4 + kf] = hmax; B.H_min[env * 4 + kf] = mn; }
   }
   // observation (uses info BEFORE the bookkeeping below, except feet_air_time which is already += dt)
@@ -1538,12 +1541,13 @@ DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, i
     const float* v = Z.fvel; const float* pf = Z.fpos;
     const float vxy2 = v[0] * v[0] + v[1] * v[1];
     vals[7] = vxy2 * (float)contact;
-    vals[8] = fabsf(pf[2] - (hmax + GC.swing_height)) * sqrtf(sqrtf(vxy2));
+    vals[8] = (GC.variant ? fabsf(Z.fworld[2] - (hmax - GC.base_feet_distance + GC.swing_height))   // world-frame foot height, joystick.py:569-572
+                          : fabsf(pf[2] - (hmax + GC.swing_height))) * sqrtf(sqrtf(vxy2));
     const float rz = gait_get_z(phase, hmax + GC.swing_height, GC.base_feet_distance);
     vals[9] = (pf[2] - rz) * (pf[2] - rz);
     const int swing_mask = (phase / (2.f * PGTT_PI)) >= 0.5f;
     vals[10] = (pf[2] - GC.swing_height) * (pf[2] - GC.swing_height) * (float)swing_mask;
-    vals[11] = (air - 0.1f) * (float)first_contact;
+    vals[11] = (air - (GC.variant ? 0.5f : 0.1f)) * (float)first_contact;   // joystick.py:591 vs joystick_pgtt.py:597
     vals[12] = (float)(swing_mask && contact);
     vals[13] = pf[0] * pf[0] + pf[1] * pf[1];
     const float er = swing_peak / GC.swing_height - 1.f;
@@ -1660,8 +1664,8 @@ DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, i
       for (int i = g; i < 9; i += 4) B.site_xmat[env * 9 + i] = B.first_site_xmat[env * 9 + i];
       for (int i = g; i < NCON; i += 4) B.contact_dist[env * NCON + i] = B.first_contact_dist[env * NCON + i];
       for (int i = g; i < 2 * NCON; i += 4) B.contact_geom[env * NCON * 2 + i] = B.first_contact_geom[env * NCON * 2 + i];
-      for (int i = g; i < NOBS; i += 4) B.obs_state[(size_t)env * NOBS + i] = B.first_obs_state[(size_t)env * NOBS + i];
-      for (int i = g; i < NPRIV; i += 4) B.obs_priv[(size_t)env * NPRIV + i] = B.first_obs_priv[(size_t)env * NPRIV + i];
+      for (int i = g; i < GC.nobs; i += 4) B.obs_state[(size_t)env * GC.nobs + i] = B.first_obs_state[(size_t)env * GC.nobs + i];
+      for (int i = g; i < GC.npriv; i += 4) B.obs_priv[(size_t)env * GC.npriv + i] = B.first_obs_priv[(size_t)env * GC.npriv + i];
       if (g == 0) B.time[env] = 0.f;
     }
   }

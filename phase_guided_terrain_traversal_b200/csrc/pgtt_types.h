@@ -46,6 +46,9 @@ struct ModelConst {
   float cmd_u_max[3], cmd_u_min[3], cmd_b[3], gait_freq[2];
   float soft_lo[12], soft_hi[12], default_pose[12], home_qpos[NQ];
   int history_update_steps, episode_length, rng_partitionable;
+  // task variant: 0 = phase-guided (go2/joystick_pgtt.py, obs 171 / 215), 1 = baseline (go2/joystick.py, obs 162 / 206: no phase,
+  // no gait_freq; H_max = quadrant max; world-frame clearance; air-time threshold 0.5)
+  int variant, nobs, npriv;
 };
 
 // Device pointers, all [N][dim] row-major (see include/pgtt_b200.h:pgtt_buffers).

@@ -87,8 +87,9 @@ class Go2Env:
     """Base class for the GO2 (go2/base.py:45-113)."""
 
     def __init__(self, xml_path: str, config, config_overrides: Optional[Dict[str, Any]] = None, task: Optional[str] = None,
-                 num_envs: Optional[int] = None, device: int = 0, rng_partitionable: bool = True):
+                 num_envs: Optional[int] = None, device: int = 0, rng_partitionable: bool = True, variant: int = 0):
         self._config = copy.deepcopy(config)
+        self._variant = int(variant)   # 0 = go2/joystick_pgtt.py, 1 = go2/joystick.py (baseline task)
         if config_overrides:
             self._config.update_from_flattened_dict(config_overrides)
         self._xml_path = xml_path
@@ -124,7 +125,7 @@ class Go2Env:
         cfg = copy.deepcopy(self._config)
         if self._episode_length is not None:
             cfg.episode_length = int(self._episode_length)
-        self._abi = AbiEnv(self._mj_model, cfg, n, device=self._device, backend="torch", rng_partitionable=self._rng_partitionable)
+        self._abi = AbiEnv(self._mj_model, cfg, n, device=self._device, backend="torch", rng_partitionable=self._rng_partitionable, variant=self._variant)
         self._num_envs = n
         self._randomized = False
         self._state = None
@@ -246,7 +247,8 @@ class Go2Env:
 
     @property
     def observation_size(self):
-        return {"state": (nat.BUFFER_FIELDS[13][2],), "privileged_state": (nat.BUFFER_FIELDS[14][2],)}
+        nobs = nat.BUFFER_FIELDS[13][2] - (9 if self._variant else 0)
+        return {"state": (nobs,), "privileged_state": (nobs + 44,)}
 
     @property
     def unwrapped(self):

@@ -195,12 +195,13 @@ class PPOTrainer:
         self.mb = self.segments // cfg.num_minibatches                      # local segments per minibatch
         gen = torch.Generator(device=self.dev)
         gen.manual_seed(cfg.seed)                                           # same init on every rank
-        self.policy_params = lecun_uniform_params((171, *cfg.policy_hidden_layer_sizes, 24), gen, self.dev)
-        self.value_params = lecun_uniform_params((215, *cfg.value_hidden_layer_sizes, 1), gen, self.dev)
+        nobs, npriv = self.abi.nobs, self.abi.npriv                          # 171 / 215, or 162 / 206 for the baseline task
+        self.policy_params = lecun_uniform_params((nobs, *cfg.policy_hidden_layer_sizes, 24), gen, self.dev)
+        self.value_params = lecun_uniform_params((npriv, *cfg.value_hidden_layer_sizes, 1), gen, self.dev)
         self.params = [*self.policy_params[0], *self.policy_params[1], *self.value_params[0], *self.value_params[1]]
         self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=cfg.use_cuda_graph, foreach=True)
-        self.norm_state, self.norm_priv = RunningStats(171, self.dev), RunningStats(215, self.dev)
-        self.net = PolicyNet((171, *cfg.policy_hidden_layer_sizes, 24), device=self.abi.device)
+        self.norm_state, self.norm_priv = RunningStats(nobs, self.dev), RunningStats(npriv, self.dev)
+        self.net = PolicyNet((nobs, *cfg.policy_hidden_layer_sizes, 24), device=self.abi.device)
         self.collector = RolloutCollector(wenv, self.net, unroll_length=cfg.unroll_length, seed=cfg.seed * 7919 + self.rank)
         self.state = state
         self.gen = torch.Generator(device=self.dev)

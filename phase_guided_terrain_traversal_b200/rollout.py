@@ -50,7 +50,7 @@ class RolloutCollector:
         self.torch = torch
         N, T, dev = abi.N, self.T, abi.torch_device
         f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        self.buf = Rollout(f(T + 1, N, 171), f(T + 1, N, 215), f(T, N, 12), f(T, N, 12), f(T, N), f(T, N), f(T, N), f(T, N))
+        self.buf = Rollout(f(T + 1, N, abi.nobs), f(T + 1, N, abi.npriv), f(T, N, 12), f(T, N, 12), f(T, N), f(T, N), f(T, N), f(T, N))
         self._step = 0      # exploration-noise counter: advances by T per collect
 
     def collect(self, state=None, deterministic: bool = False) -> tuple:

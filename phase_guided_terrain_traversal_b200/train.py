@@ -22,16 +22,17 @@ def run_training(args):
     import torch
     import torch.distributed as dist
     from . import ppo, registry, sharding, terrain, wrapper
-    from .go2 import joystick_pgtt, randomize, randomize_simple
-    from .go2.configs import default_config
+    from .go2 import joystick, joystick_pgtt, randomize, randomize_simple
+    from .go2.configs import baseline_config, default_config
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     env_name = "Go2"
-    registry.register_environment(env_name, functools.partial(joystick_pgtt.Joystick, task=args.task_name, device=local), default_config)   # train.py:115-116
-    env_cfg = default_config()                                                                                       # train.py:119-129
+    joy, cfg_fn = (joystick_pgtt, default_config) if args.method == "pgtt" else (joystick, baseline_config)                     # train.py:111-114,119-122
+    registry.register_environment(env_name, functools.partial(joy.Joystick, task=args.task_name, device=local), cfg_fn)          # train.py:115-116
+    env_cfg = cfg_fn()                                                                                       # train.py:119-129
     env_cfg.command_config.u_max = [0.6, 0.6, 1.0]
     env_cfg.command_config.u_min = [-0.6, -0.6, -1.0]
     env_cfg.gait_freq = [1, 3]
@@ -77,8 +78,8 @@ def main():
     p.add_argument("--out", type=str, default=None)
     p.add_argument("--matmul_precision", type=str, default="highest", help="learner GEMMs: highest (fp32, reference) or high (TF32)")
     args = p.parse_args()
-    if args.method != "pgtt":
-        raise SystemExit("only --method pgtt is built (the baseline task variant is a SURVEY 8f-3 'next' row)")
+    if args.method not in ("pgtt", "baseline"):
+        raise SystemExit("--method must be pgtt or baseline")
     run_training(args)
 
 

@@ -348,11 +348,14 @@ class PhysicsShim:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_reference_env(task, cfg, model, State):
+def make_reference_env(task, cfg, model, State, method="pgtt"):
     """Joystick instance of the REFERENCE class, constructed without MuJoCo: the attributes
     Go2Env.__init__ (go2/base.py:45-113) derives from the compiled MJCF are filled from model.py."""
     sys.path.insert(0, str(REF))
-    import go2.joystick_pgtt as ref_joy
+    if method == "baseline":
+        import go2.joystick as ref_joy          # the non-phase comparison task (train.py:111-114)
+    else:
+        import go2.joystick_pgtt as ref_joy
     env = object.__new__(ref_joy.Joystick)
     env._config = cfg
     env._mj_model = model
@@ -393,20 +396,21 @@ def snapshot(state, out, tag, reward_keys):
     out[f"{tag}/qvel"] = np.asarray(state.data.qvel, np.float32)
 
 
-def run_case(name, task, level, dr, seeds, n_steps, out_dir):
-    from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
+def run_case(name, task, level, dr, seeds, n_steps, out_dir, method="pgtt"):
+    from phase_guided_terrain_traversal_b200.go2.configs import baseline_config, default_config, training_overrides
     from phase_guided_terrain_traversal_b200._native import REWARD_KEYS
-    cfg = training_overrides(default_config())
+    cfg = training_overrides(baseline_config() if method == "baseline" else default_config())   # train.py:119-129 for both methods
+    variant = int(method == "baseline")
     model = gm.compile_model(task)
     table = terrain.load_terrain(level) if task == "stairs" else None
     out = {"meta/task": task, "meta/level": level or "", "meta/dr": int(dr), "meta/seeds": np.array(seeds), "meta/n_steps": n_steps,
-           "meta/partitionable": int(PART)}
+           "meta/partitionable": int(PART), "meta/variant": variant}
     for seed in seeds:
-        orc = Oracle(model, cfg, 1, "f32", rng_partitionable=PART)
+        orc = Oracle(model, cfg, 1, "f32", rng_partitionable=PART, variant=variant)
         dr_key = prng.env_keys(11, 1, offset=seed)
         orc.randomize(dr_key, table, bool(dr))
         PHYSICS.bind(orc, model)
-        env = make_reference_env(task, cfg, model, STATE)
+        env = make_reference_env(task, cfg, model, STATE, method)
         reset_key = prng.env_keys(12, 1, offset=seed)[0]
         state = env.reset(reset_key)
         tag = f"seed{seed}"
@@ -486,3 +490,4 @@ if __name__ == "__main__":
     run_case("flat", "flat_terrain", None, dr=1, seeds=[0, 1], n_steps=12, out_dir=out_dir)
     run_case("stairs_level07", "stairs", "level07", dr=1, seeds=[0, 1, 2], n_steps=12, out_dir=out_dir)
     run_case("stairs_level1_nodr", "stairs", "level1", dr=0, seeds=[3], n_steps=8, out_dir=out_dir)
+    run_case("baseline_stairs_level07", "stairs", "level07", dr=1, seeds=[0, 1], n_steps=12, out_dir=out_dir, method="baseline")

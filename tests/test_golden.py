@@ -22,7 +22,7 @@ from phase_guided_terrain_traversal_b200 import prng, terrain
 from phase_guided_terrain_traversal_b200.go2 import gait, utility
 
 GOLD = Path(__file__).resolve().parent / "golden"
-CASES = ["flat", "stairs_level07", "stairs_level1_nodr"]
+CASES = ["flat", "stairs_level07", "stairs_level1_nodr", "baseline_stairs_level07"]
 
 # golden info key -> (oracle field, abi field)
 INFO_MAP = {"command": ("command", "command"), "step": ("step", "step"), "steps_until_next_cmd": ("steps_until_next_cmd", "steps_until_next_cmd"),
@@ -78,9 +78,13 @@ def test_gait_and_yaw_closed_form():
 
 
 # ---- task layer --------------------------------------------------------------------------------------------
-def _cfg():
-    from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
-    return training_overrides(default_config())
+def _cfg(variant=0):
+    from phase_guided_terrain_traversal_b200.go2.configs import baseline_config, default_config, training_overrides
+    return training_overrides(baseline_config() if variant else default_config())
+
+
+def _variant(g):
+    return int(g["meta/variant"]) if "meta/variant" in g.files else 0
 
 
 def _tol(name):
@@ -115,15 +119,18 @@ def test_oracle_matches_reference_task_code(case):
     """(a): the oracle's own reset/step (restated task layer) against the reference-code fixtures."""
     g = np.load(GOLD / f"task_layer_{case}.npz")
     task, level, dr = str(g["meta/task"]), str(g["meta/level"]), bool(g["meta/dr"])
-    cfg, m = _cfg(), gm.compile_model(task)
+    var = _variant(g)
+    cfg, m = _cfg(var), gm.compile_model(task)
     table = terrain.load_terrain(level) if task == "stairs" else None
     for seed in g["meta/seeds"]:
         st = f"seed{seed}"
-        o = Oracle(m, cfg, 1, "f32", rng_partitionable=bool(g["meta/partitionable"]))
+        o = Oracle(m, cfg, 1, "f32", rng_partitionable=bool(g["meta/partitionable"]), variant=var)
         o.randomize(g[st + "/dr_key"][None], table, dr)
         assert int(o.get("terrain_index")[0, 0]) == int(g[st + "/terrain_index"])
         o.reset(g[st + "/reset_key"][None])
-        get = lambda of, af=None: o.get(of)[0]
+        nobs = 162 if var else 171
+        cut = {"obs_state": nobs, "obs_priv": nobs + 44}          # the oracle keeps max-size arrays; the variant fills a prefix
+        get = lambda of, af=None: o.get(of)[0][:cut.get(of)]
         _compare(get, g, "reset", st, "oracle")
         for s in range(int(g["meta/n_steps"])):
             o.step(g[st + "/actions"][s][None].astype(np.float64), wrapped=False)
@@ -137,11 +144,12 @@ def test_kernel_matches_reference_task_code(kind, case):
     only by fp32 operation order; a few steps stay inside the tolerances before trajectories drift."""
     g = np.load(GOLD / f"task_layer_{case}.npz")
     task, level, dr = str(g["meta/task"]), str(g["meta/level"]), bool(g["meta/dr"])
-    cfg, m = _cfg(), gm.compile_model(task)
+    var = _variant(g)
+    cfg, m = _cfg(var), gm.compile_model(task)
     table = terrain.load_terrain(level) if task == "stairs" else None
     seeds = list(g["meta/seeds"])
     n = len(seeds)
-    env = make_env(kind, m, cfg, n, rng_partitionable=bool(g["meta/partitionable"]))
+    env = make_env(kind, m, cfg, n, rng_partitionable=bool(g["meta/partitionable"]), variant=var)
     if table is not None:
         env.set_terrain(table)
     env.randomize(np.stack([g[f"seed{s}/dr_key"] for s in seeds]), dr)
@@ -174,7 +182,7 @@ def _compare_loose(get, g, tag, seed_tag, who):
         err = np.abs(got - want).max()
         assert err <= tol * max(1.0, np.abs(want).max()), (who, seed_tag, tag, name, err)
     got, want = np.asarray(get("obs_priv"), np.float64), np.asarray(g[p + "obs_privileged"], np.float64)
-    acc = slice(174, 177)
+    acc = slice(want.size - 44 + 3, want.size - 44 + 6)          # privileged extras start at nobs: linvel 3, accelerometer 3, ...
     assert np.abs(got[acc] - want[acc]).max() <= 2e-3 * max(1.0, np.abs(want[acc]).max()), (who, seed_tag, tag, "accelerometer")
     got[acc] = want[acc]
     assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (who, seed_tag, tag, "obs_privileged")

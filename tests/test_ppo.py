@@ -141,3 +141,24 @@ def test_trainer_runs_and_is_consistent_with_the_policy_kernel(train_cfg, tmp_pa
     assert [k.shape for k in d["policy"][0]] == [(171, 512), (512, 256), (256, 128), (128, 24)]
     assert [k.shape for k in d["value"][0]] == [(215, 512), (512, 256), (256, 128), (128, 1)]
     assert d["count"] == 2 * 2 * 20 * n
+
+
+@pytest.mark.gpu
+def test_baseline_task_trains(train_cfg):
+    """`--method baseline` (go2/joystick.py, obs 162 / 206): env, rollout (policy kernel with a 162-wide input) and learner."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo, prng
+    from phase_guided_terrain_traversal_b200.go2.configs import baseline_config, training_overrides
+    from phase_guided_terrain_traversal_b200.go2.joystick import Joystick
+    from phase_guided_terrain_traversal_b200.go2.randomize_simple import domain_randomize
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+    n = 256
+    env = Joystick(task="flat_terrain", config=training_overrides(baseline_config()))
+    assert env.observation_size == {"state": (162,), "privileged_state": (206,)}
+    keys = prng.env_keys(2, n)
+    wenv = wrap_for_brax_training(env, episode_length=1000, randomization_fn=lambda m: domain_randomize(m, rng=keys))
+    state = wenv.reset(keys)
+    assert tuple(state.obs["state"].shape) == (n, 162) and tuple(state.obs["privileged_state"].shape) == (n, 206)
+    tr = ppo.PPOTrainer(wenv, state, ppo.PPOConfig(num_envs=n, batch_size=64, num_minibatches=8, num_updates_per_batch=1, use_cuda_graph=False))
+    m = tr.training_step()
+    assert all(math.isfinite(v) for v in m.values()) and tr.collector.buf.obs_state.shape == (21, n, 162)
