@@ -193,6 +193,22 @@ typedef struct {
 int pgtt_rollout(pgtt_env* env, pgtt_policy* policy, int T, uint64_t seed, uint64_t step0, int deterministic,
                  const pgtt_rollout_buffers* out, void* stream);
 
+/* ---- learner helpers (brax ppo losses as driven by training/train.py:135-161) ---- */
+/* Generalised advantage estimation with brax's truncation handling (compute_gae), one thread per trajectory segment.
+ * All DEVICE, time-major: truncation / discount (= 1 - done) / reward [T][B], values [T + 1][B] (last row = bootstrap);
+ * outputs vs (value targets) and adv [T][B]. termination = (1 - discount) * (1 - truncation). */
+int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B,
+             float lambda, float gamma, float reward_scaling, float* vs, float* adv, void* stream);
+
+/* Fused PPO loss head (brax ppo losses: NormalTanh log-prob of the stored raw action, importance ratio, clipped surrogate,
+ * 0.25 MSE value loss, one-sample entropy estimate) for M = T * B transitions with A action dims, forward AND the
+ * gradients with respect to the logits [M][2A] and the value predictions [M] in one launch. adv_moments: DEVICE float[2] =
+ * (mean, std) used to normalise the advantages (std + 1e-8). sums: DEVICE float[4], zeroed by the call, receives
+ * (total loss, policy loss, value loss, entropy), each already divided by M. */
+int pgtt_ppo_head(const float* logits, const float* baseline, const float* raw_action, const float* old_log_prob, const float* adv,
+                  const float* vs, const float* eps, const float* adv_moments, int M, int A, float clip_eps, float entropy_cost,
+                  float min_std, float* grad_logits, float* grad_baseline, float* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -489,6 +489,102 @@ int pgtt_store_slot(const float* src, float* dst_base, int slot, size_t n_floats
 
 int64_t pgtt_policy_launch_count(pgtt_policy* p) { return p ? p->launches : 0; }
 
+// brax compute_gae: backward recursion over one trajectory segment per thread (coalesced across segments)
+__global__ void pgtt_gae_kernel(const float* __restrict__ trunc, const float* __restrict__ disc, const float* __restrict__ rew,
+                                const float* __restrict__ val, int T, int B, float lam, float gamma, float rscale,
+                                float* __restrict__ vs, float* __restrict__ adv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float acc = 0.f, vs_next = val[(size_t)T * B + b];
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t i = (size_t)t * B + b;
+    const float tr = trunc[i], mask = 1.f - tr, term = (1.f - disc[i]) * mask, r = rew[i] * rscale, v = val[i];
+    const float cont = gamma * (1.f - term);
+    const float delta = (r + cont * val[i + B] - v) * mask;
+    acc = delta + cont * mask * lam * acc;
+    const float vst = acc + v;
+    adv[i] = (r + cont * vs_next - v) * mask;
+    vs[i] = vst;
+    vs_next = vst;
+  }
+}
+
+int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
+             float reward_scaling, float* vs, float* adv, void* stream) {
+  if (!truncation || !discount || !reward || !values || !vs || !adv || T <= 0 || B <= 0) return pfail(PGTT_ERR_ARG, "pgtt_gae: null argument or empty shape");
+  pgtt_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
+// Fused PPO head: one thread per transition; forward terms and gradients (see include/pgtt_b200.h)
+#define HEAD_MAXA 16
+__global__ void pgtt_ppo_head_kernel(const float* __restrict__ logits, const float* __restrict__ baseline, const float* __restrict__ raw,
+                                     const float* __restrict__ old_lp, const float* __restrict__ adv, const float* __restrict__ vs,
+                                     const float* __restrict__ eps, const float* __restrict__ mom, int M, int A, float clip_eps, float c_ent,
+                                     float min_std, float* __restrict__ g_logits, float* __restrict__ g_base, float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float pol = 0.f, vl = 0.f, ent = 0.f;
+  if (i < M) {
+    const float invM = 1.0f / (float)M;
+    const float* lg = logits + (size_t)i * 2 * A;
+    float scale[HEAD_MAXA], z[HEAD_MAXA], sig[HEAD_MAXA], th[HEAD_MAXA];
+    float lp = 0.f, e = 0.f;
+    for (int j = 0; j < A; j++) {
+      const float loc = lg[j], sr = lg[A + j], x = raw[(size_t)i * A + j], ep = eps[(size_t)i * A + j];
+      const float sp = sr > 20.f ? sr : log1pf(expf(sr));
+      scale[j] = sp + min_std;
+      sig[j] = 1.f / (1.f + expf(-sr));
+      z[j] = (x - loc) / scale[j];
+      const float m2 = -2.f * x;
+      lp += -0.5f * z[j] * z[j] - logf(scale[j]) - 0.9189385332046727f - 2.f * (0.6931471805599453f - x - (m2 > 20.f ? m2 : log1pf(expf(m2))));
+      const float s = loc + scale[j] * ep, n2 = -2.f * s;
+      e += 1.4189385332046727f + logf(scale[j]) + 2.f * (0.6931471805599453f - s - (n2 > 20.f ? n2 : log1pf(expf(n2))));
+      th[j] = tanhf(s);
+    }
+    const float a = (adv[i] - mom[0]) / (mom[1] + 1e-8f);
+    const float rho = expf(lp - old_lp[i]);
+    const float rc = fminf(fmaxf(rho, 1.f - clip_eps), 1.f + clip_eps);
+    const float s1 = rho * a, s2 = rc * a;
+    pol = -fminf(s1, s2) * invM;
+    // d min(s1, s2) / d rho: s1 branch -> a; s2 branch -> a inside the clip range, 0 outside; a tie splits evenly (torch.minimum)
+    const float in_range = (rho >= 1.f - clip_eps && rho <= 1.f + clip_eps) ? 1.f : 0.f;
+    const float dmin = s1 < s2 ? a : (s1 > s2 ? a * in_range : 0.5f * (a + a * in_range));
+    const float dlp = -dmin * rho * invM;          // d total / d log-prob
+    const float verr = vs[i] - baseline[i];
+    vl = 0.25f * verr * verr * invM;
+    g_base[i] = -0.5f * verr * invM;
+    ent = e * invM;
+    const float ce = c_ent * invM;
+    float* gl = g_logits + (size_t)i * 2 * A;
+    for (int j = 0; j < A; j++) {
+      const float ep = eps[(size_t)i * A + j];
+      gl[j] = dlp * (z[j] / scale[j]) + ce * 2.f * th[j];
+      gl[A + j] = (dlp * ((z[j] * z[j] - 1.f) / scale[j]) - ce * (1.f / scale[j] - 2.f * th[j] * ep)) * sig[j];
+    }
+  }
+  // block sums -> 4 atomics per warp
+  float tot = pol + vl - c_ent * ent;
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o); pol += __shfl_xor_sync(0xffffffffu, pol, o);
+    vl += __shfl_xor_sync(0xffffffffu, vl, o); ent += __shfl_xor_sync(0xffffffffu, ent, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(sums, tot); atomicAdd(sums + 1, pol); atomicAdd(sums + 2, vl); atomicAdd(sums + 3, ent); }
+}
+
+int pgtt_ppo_head(const float* logits, const float* baseline, const float* raw_action, const float* old_log_prob, const float* adv, const float* vs,
+                  const float* eps, const float* adv_moments, int M, int A, float clip_eps, float entropy_cost, float min_std, float* grad_logits,
+                  float* grad_baseline, float* sums, void* stream) {
+  if (!logits || !baseline || !raw_action || !old_log_prob || !adv || !vs || !eps || !adv_moments || !grad_logits || !grad_baseline || !sums || M <= 0)
+    return pfail(PGTT_ERR_ARG, "pgtt_ppo_head: null argument or M <= 0");
+  if (A < 1 || A > HEAD_MAXA) return pfail(PGTT_ERR_ARG, "pgtt_ppo_head: action dim must be in 1..16");
+  PCUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), (cudaStream_t)stream));
+  pgtt_ppo_head_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, baseline, raw_action, old_log_prob, adv, vs, eps, adv_moments, M, A,
+                                                                        clip_eps, entropy_cost, min_std, grad_logits, grad_baseline, sums);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
 // generate_unroll: T x (act -> wrapped step -> record); see include/pgtt_b200.h
 int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t step0, int deterministic, const pgtt_rollout_buffers* o, void* stream) {
   if (!env || !pol || !o || T <= 0) return pfail(PGTT_ERR_ARG, "pgtt_rollout: null argument or T <= 0");

@@ -47,6 +47,7 @@ class PPOConfig:                      # names and defaults of training/train.py:
     value_hidden_layer_sizes: Sequence[int] = (512, 256, 128)
     seed: int = 0
     use_cuda_graph: bool = True
+    fused_head: bool = True               # PPO loss head + its gradients from the hand-written kernel `pgtt_ppo_head`
     # learner GEMM precision: "highest" = fp32 like the reference (jax_default_matmul_precision=highest, train.py:94),
     # "high" = TF32 tensor cores (fp32 storage and accumulation, 10-bit mantissa products)
     matmul_precision: str = "highest"
@@ -72,10 +73,27 @@ def compute_gae(truncation, termination, rewards, values, bootstrap_value, lambd
     return vs.detach(), adv.detach()
 
 
+def compute_gae_native(truncation, discount, rewards, values_all, lambda_: float, discount_factor: float, reward_scaling: float):
+    """Same quantities from the hand-written kernel `pgtt_gae` (one launch instead of ~120): CUDA float32, time-major;
+    `values_all` is [T + 1, B] with the bootstrap value in its last row."""
+    import ctypes as C
+    import torch
+    from . import _native as nat
+    lib = nat.load_library()
+    T, B = rewards.shape
+    vs, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+    args = [t.contiguous() for t in (truncation, discount, rewards, values_all)]
+    stream = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+    rc = lib.pgtt_gae(*(a.data_ptr() for a in args), T, B, lambda_, discount_factor, reward_scaling, vs.data_ptr(), adv.data_ptr(), stream)
+    if rc:
+        raise nat.PgttError(rc, lib.pgtt_policy_last_error().decode())
+    return vs, adv
+
+
 def mlp(x, kernels, biases):
     import torch
     for i, (k, b) in enumerate(zip(kernels, biases)):
-        x = x @ k + b
+        x = torch.addmm(b, x.reshape(-1, x.shape[-1]), k).reshape(*x.shape[:-1], k.shape[1])
         if i + 1 < len(kernels):
             x = torch.nn.functional.silu(x)
     return x
@@ -102,7 +120,40 @@ def tanh_normal_entropy(logits, eps, min_std: float = 0.001):
     return ent.sum(-1)
 
 
-def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_fn: Optional[Callable] = None):
+def _fused_head():
+    """torch.autograd.Function over `pgtt_ppo_head`: loss terms and the gradients wrt logits / value predictions in one launch."""
+    import ctypes as C
+    import torch
+    from . import _native as nat
+
+    class PPOHead(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, logits, baseline, raw_action, old_lp, adv, vs, eps, moments, clip_eps, entropy_cost, min_std):
+            lib = nat.load_library()
+            A = raw_action.shape[-1]
+            lg = logits.reshape(-1, 2 * A).contiguous()
+            M = lg.shape[0]
+            g_logits, g_base = torch.empty_like(lg), torch.empty(M, device=lg.device, dtype=lg.dtype)
+            sums = torch.empty(4, device=lg.device, dtype=lg.dtype)
+            flat = [t.reshape(-1).contiguous() for t in (baseline, raw_action, old_lp, adv, vs, eps)]
+            stream = C.c_void_p(torch.cuda.current_stream(lg.device).cuda_stream)
+            rc = lib.pgtt_ppo_head(lg.data_ptr(), *(t.data_ptr() for t in flat), moments.data_ptr(), M, A, clip_eps, entropy_cost, min_std,
+                                   g_logits.data_ptr(), g_base.data_ptr(), sums.data_ptr(), stream)
+            if rc:
+                raise nat.PgttError(rc, lib.pgtt_policy_last_error().decode())
+            ctx.save_for_backward(g_logits, g_base)
+            ctx.shapes = (logits.shape, baseline.shape)
+            return sums
+
+        @staticmethod
+        def backward(ctx, gs):
+            g_logits, g_base = ctx.saved_tensors
+            return (g_logits * gs[0]).reshape(ctx.shapes[0]), (g_base * gs[0]).reshape(ctx.shapes[1]), None, None, None, None, None, None, None, None, None
+
+    return PPOHead
+
+
+def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_fn: Optional[Callable] = None, fused: bool = False):
     """batch: time-major [T, B, ...] tensors with NORMALISED observations `obs`, `obs_priv` ([T + 1, B, .]) plus
     raw_action, log_prob, reward, discount, truncation ([T, B]) and entropy noise `eps` [T, B, A]."""
     import torch
@@ -116,13 +167,22 @@ def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_f
     truncation = batch["truncation"]
     termination = (1.0 - batch["discount"]) * (1.0 - truncation)
     target_lp = tanh_normal_log_prob(logits, batch["raw_action"])
-    vs, adv = compute_gae(truncation, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
+    if rewards.is_cuda and rewards.dtype == torch.float32:
+        vs, adv = compute_gae_native(truncation, batch["discount"], batch["reward"], baseline_all.detach(), cfg.gae_lambda, cfg.discounting, cfg.reward_scaling)
+    else:
+        vs, adv = compute_gae(truncation, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
     if cfg.normalize_advantage:
         if moments_fn is not None:
             mean, std = moments_fn(adv)
         else:
             mean, std = adv.mean(), adv.std(unbiased=False)
-        adv = (adv - mean) / (std + 1e-8)
+    else:
+        mean, std = torch.zeros((), device=adv.device), torch.ones((), device=adv.device) - 1e-8
+    if fused:   # hand-written head kernel: forward terms + gradients wrt logits / baseline in one launch (CUDA float32 only)
+        sums = _fused_head().apply(logits, baseline, batch["raw_action"], batch["log_prob"], adv, vs, batch["eps"],
+                                   torch.stack([mean, std]).to(torch.float32), cfg.clipping_epsilon, cfg.entropy_cost, 0.001)
+        return sums[0], {"total_loss": sums[0].detach(), "policy_loss": sums[1].detach(), "v_loss": sums[2].detach(), "entropy": sums[3].detach()}
+    adv = (adv - mean) / (std + 1e-8)
     rho = torch.exp(target_lp - batch["log_prob"])
     s1 = rho * adv
     s2 = torch.clamp(rho, 1.0 - cfg.clipping_epsilon, 1.0 + cfg.clipping_epsilon) * adv
@@ -199,7 +259,7 @@ class PPOTrainer:
         self.policy_params = lecun_uniform_params((nobs, *cfg.policy_hidden_layer_sizes, 24), gen, self.dev)
         self.value_params = lecun_uniform_params((npriv, *cfg.value_hidden_layer_sizes, 1), gen, self.dev)
         self.params = [*self.policy_params[0], *self.policy_params[1], *self.value_params[0], *self.value_params[1]]
-        self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=cfg.use_cuda_graph, foreach=True)
+        self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=cfg.use_cuda_graph, fused=True)
         self.norm_state, self.norm_priv = RunningStats(nobs, self.dev), RunningStats(npriv, self.dev)
         self.net = PolicyNet((nobs, *cfg.policy_hidden_layer_sizes, 24), device=self.abi.device)
         self.collector = RolloutCollector(wenv, self.net, unroll_length=cfg.unroll_length, seed=cfg.seed * 7919 + self.rank)
@@ -208,7 +268,7 @@ class PPOTrainer:
         self.gen.manual_seed(cfg.seed * 31 + 1 + self.rank)
         self.env_steps = 0
         self._graph = None
-        self._static: Dict = {}
+        self._data: Dict = {}
         self.metrics: Dict = {}
         self._sync_policy()
 
@@ -229,7 +289,7 @@ class PPOTrainer:
 
     def _sgd_body(self, batch):
         torch = self.torch
-        loss, m = ppo_loss(self.policy_params, self.value_params, batch, self.cfg, self._moments)
+        loss, m = ppo_loss(self.policy_params, self.value_params, batch, self.cfg, self._moments, fused=self.cfg.fused_head)
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
         if self.world > 1:
@@ -245,18 +305,27 @@ class PPOTrainer:
         self.opt.step()
         return m
 
-    def _sgd_step(self, batch):
+    def _minibatch(self):
+        """Minibatch `self._mbi` of the current epoch, gathered ON THE DEVICE from the static full-data buffers: the index
+        tensors are the only thing the host touches per SGD step, so the whole step (gather, forward, loss, backward,
+        clip, Adam) is one graph replay."""
+        idx = self._perm.index_select(0, self._mbi).reshape(-1)                          # [mb] segment ids
+        batch = {k: v.index_select(1, idx) for k, v in self._data.items()}
+        batch["eps"] = self._eps.index_select(0, self._mbi)[0]
+        return batch
+
+    def _sgd_step(self, i: int):
         torch = self.torch
+        self._mbi.fill_(i)
         graphable = self.cfg.use_cuda_graph and self.world == 1      # NCCL inside a captured graph is avoided here
         if not graphable:
-            return self._sgd_body(batch)
+            return self._sgd_body(self._minibatch())
         if self._graph is None:
-            self._static = {k: v.clone() for k, v in batch.items()}
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 for _ in range(3):                                   # warm-up outside capture (allocator, Adam state)
-                    self._sgd_body(self._static)
+                    self._sgd_body(self._minibatch())
             torch.cuda.current_stream(self.dev).wait_stream(s)
             # no garbage collection while capturing: a collected env / policy handle would run pgtt_*_destroy
             # (cudaDeviceSynchronize + cudaFree), which is illegal inside a capture
@@ -267,13 +336,11 @@ class PPOTrainer:
             try:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
-                    self._static_metrics = self._sgd_body(self._static)
+                    self._static_metrics = self._sgd_body(self._minibatch())
             finally:
                 gc.enable()
             # the warm-up steps changed the parameters: acceptable for training (three extra SGD steps on the first
             # minibatch), callers that need exact step counts construct the trainer with use_cuda_graph=False
-        for k, v in batch.items():
-            self._static[k].copy_(v)
         self._graph.replay()
         return self._static_metrics
 
@@ -281,31 +348,39 @@ class PPOTrainer:
     def training_step(self) -> Dict:
         torch, cfg = self.torch, self.cfg
         T = cfg.unroll_length
-        segs = []
-        for _ in range(self.unrolls_per_step):
+        if not self._data:       # static buffers (their addresses are baked into the captured graph)
+            nobs, npriv, S = self.abi.nobs, self.abi.npriv, self.segments
+            f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=self.dev)
+            self._data = {"obs": f(T + 1, S, nobs), "obs_priv": f(T + 1, S, npriv), "raw_action": f(T, S, 12), "log_prob": f(T, S), "reward": f(T, S),
+                          "discount": f(T, S), "truncation": f(T, S)}
+            self._perm = torch.zeros((cfg.num_minibatches, self.mb), dtype=torch.int64, device=self.dev)
+            self._eps = f(cfg.num_minibatches, T, self.mb, 12)
+            self._mbi = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        n = self.abi.N
+        for u in range(self.unrolls_per_step):
             self.state, ro = self.collector.collect()
-            segs.append({"obs": ro.obs_state.clone(), "obs_priv": ro.obs_privileged.clone(), "raw_action": ro.raw_action.clone(),
-                         "log_prob": ro.log_prob.clone(), "reward": ro.reward.clone(), "discount": ro.discount.clone(),
-                         "truncation": ro.truncation.clone()})
-            self.env_steps += T * self.abi.N * self.world
-        data = {k: torch.cat([s[k] for s in segs], 1) for k in segs[0]}            # [T(+1), segments, ...]
+            sl = slice(u * n, (u + 1) * n)
+            for k, src in (("obs", ro.obs_state), ("obs_priv", ro.obs_privileged), ("raw_action", ro.raw_action), ("log_prob", ro.log_prob),
+                           ("reward", ro.reward), ("discount", ro.discount), ("truncation", ro.truncation)):
+                self._data[k][:, sl].copy_(src)
+            self.env_steps += T * n * self.world
+        data = self._data
+        reward_mean, done_rate = data["reward"].mean(), (1.0 - data["discount"]).mean()
         if cfg.normalize_observations:
             self.norm_state.update(data["obs"][:T], self.group)
             self.norm_priv.update(data["obs_priv"][:T], self.group)
-            data["obs"] = self.norm_state.normalize(data["obs"])
-            data["obs_priv"] = self.norm_priv.normalize(data["obs_priv"])
+            data["obs"].copy_(self.norm_state.normalize(data["obs"]))
+            data["obs_priv"].copy_(self.norm_priv.normalize(data["obs_priv"]))
         last = {}
         for _ in range(cfg.num_updates_per_batch):
-            perm = torch.randperm(self.segments, generator=self.gen, device=self.dev)
+            self._perm.copy_(torch.randperm(self.segments, generator=self.gen, device=self.dev).reshape(cfg.num_minibatches, self.mb))
+            self._eps.normal_(generator=self.gen)
             for i in range(cfg.num_minibatches):
-                idx = perm[i * self.mb:(i + 1) * self.mb]
-                batch = {k: v.index_select(1, idx) for k, v in data.items()}
-                batch["eps"] = torch.randn((T, self.mb, 12), generator=self.gen, device=self.dev)
-                last = self._sgd_step(batch)
+                last = self._sgd_step(i)
         self._sync_policy()
         self.metrics = {k: float(v) for k, v in last.items()}
-        self.metrics["reward_per_step"] = float(data["reward"].mean())
-        self.metrics["episode_done_rate"] = float((1.0 - data["discount"]).mean())
+        self.metrics["reward_per_step"] = float(reward_mean)
+        self.metrics["episode_done_rate"] = float(done_rate)
         self.metrics["env_steps"] = self.env_steps
         return self.metrics
 

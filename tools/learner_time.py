@@ -6,7 +6,7 @@ from phase_guided_terrain_traversal_b200.go2.randomize import domain_randomize
 from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
 from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
 import functools
-for prec in ("highest", "high"):
+for prec in (sys.argv[1:] or ["highest", "high"]):
     n=4096
     cfg=ppo.PPOConfig(num_envs=n, matmul_precision=prec)
     env=Joystick(task="stairs", config=training_overrides(default_config()))
