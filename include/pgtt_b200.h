@@ -172,8 +172,6 @@ int pgtt_policy_set_params(pgtt_policy* p, const float* const* kernels, const fl
  * Outputs DEVICE: action [n][act_dim] = tanh(raw); raw_action [n][act_dim], log_prob [n], logits [n][2 act_dim] may be NULL. */
 int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint64_t step, int deterministic, const float* eps,
                     float* action, float* raw_action, float* log_prob, float* logits, void* stream);
-/* transition write-out: dst_base[slot][0..n_floats) <- src[0..n_floats) (both DEVICE) */
-int pgtt_store_slot(const float* src, float* dst_base, int slot, size_t n_floats, void* stream);
 int64_t pgtt_policy_launch_count(pgtt_policy* p);
 
 /* One launch that files the current step's results into a time-major rollout slot: obs_state_dst / obs_priv_dst

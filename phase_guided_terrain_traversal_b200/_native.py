@@ -199,7 +199,6 @@ def declare(lib):
         lib.pgtt_policy_destroy.argtypes = [vp]
         lib.pgtt_policy_set_params.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, vp]
         lib.pgtt_policy_act.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
-        lib.pgtt_store_slot.argtypes = [vp, vp, C.c_int, C.c_size_t, vp]
         lib.pgtt_policy_launch_count.argtypes = [vp]
         lib.pgtt_policy_launch_count.restype = C.c_int64
         lib.pgtt_rollout.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(RolloutBuffers), vp]
@@ -211,7 +210,7 @@ def declare(lib):
 ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
     "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
-    "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act", "pgtt_store_slot",
+    "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act",
     "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_ppo_head",
 ]
 

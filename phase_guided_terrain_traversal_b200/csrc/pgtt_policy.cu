@@ -347,12 +347,6 @@ pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, un
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// HBM-bound copy of one rollout slot (transition write-out in the learner's [T, N, .] layout)
-__global__ void pgtt_store_slot_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i];
-}
-
 // ----------------------------------------------------------------------------------------------
 // host side + C ABI
 // ----------------------------------------------------------------------------------------------
@@ -474,16 +468,6 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
                                                                         deterministic, eps, action, raw_action, log_prob, logits);
   PCUDA(cudaGetLastError());
   p->launches++;
-  return PGTT_OK;
-}
-
-// dst[slot] <- src for a [T][n_floats] rollout buffer (both DEVICE)
-int pgtt_store_slot(const float* src, float* dst_base, int slot, size_t n_floats, void* stream) {
-  if (!src || !dst_base) return pfail(PGTT_ERR_ARG, "pgtt_store_slot: null argument");
-  const int threads = 256;
-  const size_t blocks = (n_floats + threads - 1) / threads;
-  pgtt_store_slot_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(src, dst_base + (size_t)slot * n_floats, n_floats);
-  PCUDA(cudaGetLastError());
   return PGTT_OK;
 }
 
