@@ -40,12 +40,16 @@
 struct PolicyLayer {
   int K, N, Kp, Np, Kc, nchunks;   // true sizes, padded sizes, K per chunk
   size_t w_off, b_off;             // offsets (elements) into the packed weight / bias arrays
+  // cluster layout (4 CTAs per 128-row tile, each owning Ns = Np / 4 output columns; the head layer stays whole on rank 0)
+  int Ns, cKc, cnchunks;
+  size_t cw_off, cw_rstride;       // element offset of rank 0's chunks in `cw`, elements per rank
 };
 
 struct PolicyParams {
   int n_layers, obs_dim, act_dim;
   PolicyLayer L[POL_MAXLAYERS];
   const __nv_bfloat16* w;   // packed chunks, canonical UMMA K-major layout
+  const __nv_bfloat16* cw;  // the same weights packed per cluster rank (NULL: cluster kernel unavailable for these sizes)
   const float* bias;        // padded biases
   const float* mean;        // [obs_dim]
   const float* inv_std;     // [obs_dim]
@@ -348,11 +352,214 @@ pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, un
 }
 
 // ----------------------------------------------------------------------------------------------
+// cluster variant: 4 CTAs (one thread-block cluster) share a 128-row tile. Each CTA computes a quarter of every hidden
+// layer's columns (a quarter of the MMAs, of the weight stream and of the SiLU epilogue) and writes its bf16 activation
+// slice into the shared memory of all four CTAs through distributed shared memory (mapa + st.shared::cluster); two
+// cluster barriers per layer order "everybody's MMAs have read the old A operand" -> slice exchange -> next layer. The
+// 24-wide head runs on rank 0. 4096 rows occupy 128 SMs instead of 32.
+// ----------------------------------------------------------------------------------------------
+#define POL_CL 4
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  // not .aligned: the control warp reaches it diverged (lane 0 issues the MMAs, lanes 1..31 arrive early)
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cta_addr, uint32_t rank, uint4 v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(cta_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __cluster_dims__(POL_CL, 1, 1) __launch_bounds__(POL_THREADS, 1)
+pgtt_policy_cluster_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step,
+                           int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
+                           float* __restrict__ log_prob, float* __restrict__ logits_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + POL_A_BYTES;
+  float* sBias = reinterpret_cast<float*>(smem + POL_A_BYTES + POL_NBUF * POL_BCHUNK);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBias + POL_MAXBIAS);
+  uint64_t* empty = full + POL_NBUF;
+  uint64_t* layer_done = empty + POL_NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_rank();
+  const int row0 = (blockIdx.x / POL_CL) * POL_TM;
+  const int my_layers = rank == 0 ? P.n_layers : P.n_layers - 1;      // the head layer runs on rank 0 only
+
+  if (tid == 0) {
+    for (int i = 0; i < POL_NBUF; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(layer_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  __syncthreads();
+  int ld_l = 0, ld_c = 0, ld_g = 0;
+  auto top_up = [&](int upto) {
+    while (ld_l < my_layers && ld_g < upto) {
+      const PolicyLayer& Ln = P.L[ld_l];
+      const int b = ld_g % POL_NBUF;
+      if (ld_g >= POL_NBUF) mbar_wait(&empty[b], (uint32_t)((ld_g / POL_NBUF - 1) & 1));
+      const uint32_t bytes = (uint32_t)(Ln.Ns * Ln.cKc * 2);
+      const __nv_bfloat16* src = P.cw + Ln.cw_off + (size_t)rank * Ln.cw_rstride + (size_t)ld_c * (bytes / 2);
+      mbar_expect_tx(&full[b], bytes);
+      bulk_g2s(sB + (size_t)b * POL_BCHUNK, src, bytes, &full[b]);
+      ld_g++;
+      if (++ld_c == Ln.cnchunks) { ld_c = 0; ld_l++; }
+    }
+  };
+  if (tid == POL_CTRL_TID) top_up(POL_NBUF - 1);
+  {
+    int nb = 0;
+    for (int l = 0; l < P.n_layers; l++) nb += P.L[l].Np;
+    for (int i = tid; i < nb; i += POL_THREADS) sBias[i] = __ldg(P.bias + i);
+  }
+  {  // every CTA of the cluster stages the whole normalised observation tile (layer 0 needs all of K)
+    const PolicyLayer& L0 = P.L[0];
+    const uint32_t sbo = (uint32_t)L0.Kp * 16u;
+    const int kgroups = L0.Kp >> 3;
+    for (int rg = warp; rg < POL_TM / 8; rg += POL_THREADS / 32) {
+      const int r = rg * 8 + (lane & 7), row = row0 + r;
+      const float* orow = obs + (size_t)row * P.obs_dim;
+      for (int kg = lane >> 3; kg < kgroups; kg += 4) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int k = kg * 8 + i;
+          v[i] = (row < n_rows && k < L0.K) ? (__ldg(orow + k) - __ldg(P.mean + k)) * __ldg(P.inv_std + k) : 0.f;
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); pk[i] = *reinterpret_cast<const uint32_t*>(&h); }
+        *reinterpret_cast<uint4*>(sA + (uint32_t)rg * sbo + (uint32_t)kg * 128u + (uint32_t)(lane & 7) * 16u) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  int g = 0;
+  for (int l = 0; l < P.n_layers; l++) {
+    const PolicyLayer& L = P.L[l];
+    const bool last = l + 1 == P.n_layers;
+    if (last && rank != 0) break;                       // ranks 1..3 are done: nobody touches their shared memory any more
+    if (tid == POL_CTRL_TID) {
+      const uint32_t a_sbo = (uint32_t)L.Kp * 16u, b_sbo = (uint32_t)L.cKc * 16u;
+      for (int c = 0; c < L.cnchunks; c++) {
+        const int gc = g + c, bi = gc % POL_NBUF;
+        top_up(gc + POL_NBUF - 1);
+        mbar_wait(&full[bi], (uint32_t)((gc / POL_NBUF) & 1));
+        tc_fence_after();
+        const uint8_t* buf = sB + (size_t)bi * POL_BCHUNK;
+        const int nslices = L.cKc / 16;
+        for (int s = 0; s < nslices; s++) {
+          const int kslice = c * nslices + s;
+          umma_bf16(tmem, make_desc(smem_u32(sA) + (uint32_t)kslice * 256u, 128u, a_sbo), make_desc(smem_u32(buf) + (uint32_t)s * 256u, 128u, b_sbo),
+                    make_idesc(POL_TM, L.Ns), (uint32_t)(kslice > 0));
+        }
+        umma_commit(&empty[bi]);
+      }
+      umma_commit(layer_done);
+    }
+    g += L.cnchunks;
+    const int q = warp & 3, cq = warp >> 2;
+    const int r = q * 32 + lane, row = row0 + r;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const bool epi = warp < POL_EPI_THREADS / 32;
+    if (epi) { mbar_wait(layer_done, (uint32_t)(l & 1)); tc_fence_after(); }
+    if (!last) {
+      // (A) every CTA of the cluster has finished the MMAs that read the current A operand
+      cluster_sync_all();
+      if (epi) {
+        const float* bias = sBias + L.b_off + rank * L.Ns;
+        const uint32_t sbo_next = (uint32_t)P.L[l + 1].Kp * 16u;     // == Np of this layer
+        const bool to_all = l + 2 < P.n_layers;                        // the head's input is only needed by rank 0
+        for (int n0 = cq * 32; n0 < L.Ns; n0 += 128) {
+          float vv[32];
+          tmem_ld32(trow + (uint32_t)n0, vv);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int n = n0 + 8 * j + 2 * i, ng = rank * L.Ns + n;
+              float a = vv[8 * j + 2 * i] + bias[n], b = vv[8 * j + 2 * i + 1] + bias[n + 1];
+              a = (ng < L.N) ? __fdividef(a, 1.f + __expf(-a)) : 0.f;          // SiLU (swish)
+              b = (ng + 1 < L.N) ? __fdividef(b, 1.f + __expf(-b)) : 0.f;
+              const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            const uint32_t kg = (uint32_t)((rank * L.Ns + n0) >> 3) + (uint32_t)j;
+            const uint32_t addr = smem_u32(sA) + (uint32_t)(r >> 3) * sbo_next + kg * 128u + (uint32_t)(r & 7) * 16u;
+            const uint4 val = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (to_all) {
+#pragma unroll
+              for (int d = 0; d < POL_CL; d++) st_cluster_v4(addr, (uint32_t)d, val);
+            } else {
+              st_cluster_v4(addr, 0u, val);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores (local and remote) -> the async proxy that feeds the MMAs
+        tc_fence_before();
+      }
+      // (B) all slices have arrived everywhere
+      cluster_sync_all();
+      tc_fence_after();
+    } else {
+      if (epi) {
+        const float* bias = sBias + L.b_off;
+        float out[32];
+        tmem_ld32(trow, out);
+        const int A = P.act_dim, per = (A + 3) >> 2;
+        float* lp_part = reinterpret_cast<float*>(sA);
+        float lp = 0.f;
+        if (row < n_rows) {
+          for (int j = cq * per; j < (cq + 1) * per && j < A; j++) {
+            float ol = 0.f, os = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i++) { ol = (i == j) ? out[i] : ol; os = (i == A + j) ? out[i] : os; }
+            const float loc = ol + bias[j], sr = os + bias[A + j];
+            if (logits_out) { logits_out[(size_t)row * 2 * A + j] = loc; logits_out[(size_t)row * 2 * A + A + j] = sr; }
+            const float scale = (sr > 20.f ? sr : log1pf(expf(sr))) + 0.001f;
+            float e = 0.f;
+            if (!deterministic) e = eps_in ? eps_in[(size_t)row * A + j] : normal_draw(seed, step, (uint32_t)row, (uint32_t)j);
+            const float raw = loc + scale * e;
+            const float m2 = -2.f * raw;
+            const float sp = m2 > 20.f ? m2 : log1pf(expf(m2));
+            lp += -0.5f * e * e - logf(scale) - 0.9189385332046727f - 2.f * (0.6931471805599453f - raw - sp);
+            action[(size_t)row * A + j] = tanhf(raw);
+            if (raw_action) raw_action[(size_t)row * A + j] = raw;
+          }
+        }
+        lp_part[cq * POL_TM + r] = lp;
+        asm volatile("bar.sync 1, %0;" ::"r"(POL_EPI_THREADS) : "memory");
+        if (cq == 0 && row < n_rows && log_prob) log_prob[row] = ((lp_part[r] + lp_part[POL_TM + r]) + lp_part[2 * POL_TM + r]) + lp_part[3 * POL_TM + r];
+        tc_fence_before();
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// ----------------------------------------------------------------------------------------------
 // host side + C ABI
 // ----------------------------------------------------------------------------------------------
 struct pgtt_policy {
   int device;
   PolicyParams P;
+  __nv_bfloat16* cw_dev;
+  size_t cw_elems;
+  bool use_cluster;
   __nv_bfloat16* w_dev;
   float *bias_dev, *mean_dev, *istd_dev;
   size_t w_elems, b_elems;
@@ -383,7 +590,7 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
   pgtt_policy* p = new pgtt_policy();
   memset(&p->P, 0, sizeof(p->P));
   p->device = device; p->has_params = false; p->launches = 0;
-  p->w_dev = nullptr; p->bias_dev = p->mean_dev = p->istd_dev = nullptr;
+  p->w_dev = nullptr; p->cw_dev = nullptr; p->bias_dev = p->mean_dev = p->istd_dev = nullptr;
   PolicyParams& P = p->P;
   P.n_layers = n_layers; P.obs_dim = sizes[0]; P.act_dim = sizes[n_layers] / 2;
   size_t w_off = 0, b_off = 0;
@@ -403,6 +610,21 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
     L.w_off = w_off; L.b_off = b_off;
     w_off += (size_t)L.Np * L.Kp; b_off += L.Np;
   }
+  {  // cluster layout: hidden layers split 4 ways over the columns, the head whole on rank 0
+    size_t cw_off = 0;
+    for (int l = 0; l < n_layers; l++) {
+      PolicyLayer& L = P.L[l];
+      const bool head = l + 1 == n_layers;
+      L.Ns = head ? L.Np : L.Np / POL_CL;
+      int kc = (POL_BCHUNK / 2 / L.Ns) / 16 * 16;
+      if (kc > L.Kp) kc = L.Kp;
+      while (kc > 16 && L.Kp % kc != 0) kc -= 16;
+      L.cKc = kc; L.cnchunks = L.Kp / kc;
+      L.cw_off = cw_off; L.cw_rstride = head ? 0 : (size_t)L.Ns * L.Kp;
+      cw_off += (size_t)L.Ns * L.Kp * (head ? 1 : POL_CL);
+    }
+    p->cw_elems = cw_off;
+  }
   for (int l = 0; l + 1 < n_layers; l++)
     if (P.L[l].Np % 128 != 0) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: hidden widths must be multiples of 128"); }
   if (b_off > POL_MAXBIAS) { delete p; return pfail(PGTT_ERR_ARG, "pgtt_policy_create: total layer width above 1024"); }
@@ -410,10 +632,14 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
   p->w_elems = w_off; p->b_elems = b_off;
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->w_dev, w_off * 2) != cudaSuccess || cudaMalloc(&p->bias_dev, b_off * 4) != cudaSuccess ||
       cudaMalloc(&p->mean_dev, P.obs_dim * 4) != cudaSuccess || cudaMalloc(&p->istd_dev, P.obs_dim * 4) != cudaSuccess ||
-      cudaFuncSetAttribute(pgtt_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POL_SMEM) != cudaSuccess) {
+      cudaMalloc(&p->cw_dev, p->cw_elems * 2) != cudaSuccess ||
+      cudaFuncSetAttribute(pgtt_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POL_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(pgtt_policy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POL_SMEM) != cudaSuccess) {
     delete p; return pfail(PGTT_ERR_CUDA, std::string("pgtt_policy_create: ") + cudaGetErrorString(cudaGetLastError()));
   }
-  P.w = p->w_dev; P.bias = p->bias_dev; P.mean = p->mean_dev; P.inv_std = p->istd_dev;
+  P.w = p->w_dev; P.cw = p->cw_dev; P.bias = p->bias_dev; P.mean = p->mean_dev; P.inv_std = p->istd_dev;
+  p->use_cluster = true;     // PGTT_POLICY_CLUSTER=0 selects the single-CTA-per-tile kernel
+  if (const char* e = getenv("PGTT_POLICY_CLUSTER")) p->use_cluster = atoi(e) != 0;
   *out = p;
   return PGTT_OK;
 }
@@ -421,7 +647,7 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
 int pgtt_policy_destroy(pgtt_policy* p) {
   if (!p) return PGTT_OK;
   cudaSetDevice(p->device); cudaDeviceSynchronize();
-  cudaFree(p->w_dev); cudaFree(p->bias_dev); cudaFree(p->mean_dev); cudaFree(p->istd_dev);
+  cudaFree(p->cw_dev); cudaFree(p->w_dev); cudaFree(p->bias_dev); cudaFree(p->mean_dev); cudaFree(p->istd_dev);
   delete p;
   return PGTT_OK;
 }
@@ -444,11 +670,23 @@ int pgtt_policy_set_params(pgtt_policy* p, const float* const* kernels, const fl
       }
     for (int n = 0; n < L.N; n++) b[L.b_off + n] = biases[l][n];
   }
+  std::vector<uint16_t> cw(p->cw_elems, 0);
+  for (int l = 0; l < P.n_layers; l++) {
+    const PolicyLayer& L = P.L[l];
+    const size_t chunk_elems = (size_t)L.Ns * L.cKc;
+    for (int k = 0; k < L.K; k++)
+      for (int n = 0; n < L.N; n++) {
+        const int rank = n / L.Ns, nn = n % L.Ns, c = k / L.cKc, kk = k % L.cKc;
+        const size_t off_bytes = (size_t)(nn >> 3) * (L.cKc * 16) + (size_t)(kk >> 3) * 128 + (size_t)(nn & 7) * 16 + (size_t)(kk & 7) * 2;
+        cw[L.cw_off + (size_t)rank * L.cw_rstride + c * chunk_elems + off_bytes / 2] = f2bf(kernels[l][(size_t)k * L.N + n]);
+      }
+  }
   if (obs_mean) for (int i = 0; i < P.obs_dim; i++) mean[i] = obs_mean[i];
   if (obs_std) for (int i = 0; i < P.obs_dim; i++) istd[i] = 1.0f / obs_std[i];
   PCUDA(cudaSetDevice(p->device));
   PCUDA(cudaDeviceSynchronize());
   PCUDA(cudaMemcpy(p->w_dev, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+  PCUDA(cudaMemcpy(p->cw_dev, cw.data(), cw.size() * 2, cudaMemcpyHostToDevice));
   PCUDA(cudaMemcpy(p->bias_dev, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
   PCUDA(cudaMemcpy(p->mean_dev, mean.data(), mean.size() * 4, cudaMemcpyHostToDevice));
   PCUDA(cudaMemcpy(p->istd_dev, istd.data(), istd.size() * 4, cudaMemcpyHostToDevice));
@@ -464,8 +702,12 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
   if (!p || !obs || !action || n <= 0) return pfail(PGTT_ERR_ARG, "pgtt_policy_act: null argument or n <= 0");
   if (!p->has_params) return pfail(PGTT_ERR_STATE, "pgtt_policy_act: pgtt_policy_set_params first");
   const int blocks = (n + POL_TM - 1) / POL_TM;
-  pgtt_policy_kernel<<<blocks, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
-                                                                        deterministic, eps, action, raw_action, log_prob, logits);
+  if (p->use_cluster)
+    pgtt_policy_cluster_kernel<<<blocks * POL_CL, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
+                                                                                          deterministic, eps, action, raw_action, log_prob, logits);
+  else
+    pgtt_policy_kernel<<<blocks, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
+                                                                          deterministic, eps, action, raw_action, log_prob, logits);
   PCUDA(cudaGetLastError());
   p->launches++;
   return PGTT_OK;
