@@ -29,7 +29,7 @@ def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 
     track_lin = torch.zeros(n, device=dev)
     track_ang = torch.zeros(n, device=dev)
     metrics = col.abi.buf["metrics"]
-    obs_sum = obs_sq = None
+    obs_sum = obs_sq = priv_sum = priv_sq = None
     obs_cnt = 0
     steps = 0
     while steps < episode_length:
@@ -46,6 +46,9 @@ def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 
             obs_sum = o.sum(0) if obs_sum is None else obs_sum + o.sum(0)
             obs_sq = (o * o).sum(0) if obs_sq is None else obs_sq + (o * o).sum(0)
             obs_cnt += o.shape[0]
+            pv = ro.obs_privileged[:-1].reshape(-1, ro.obs_privileged.shape[-1]).double()
+            priv_sum = pv.sum(0) if priv_sum is None else priv_sum + pv.sum(0)
+            priv_sq = (pv * pv).sum(0) if priv_sq is None else priv_sq + (pv * pv).sum(0)
         steps += ro.reward.shape[0]
     # tracking rewards of the first episode: episode_metrics is reset by the wrapper at episode ends, so accumulate from
     # the per-step metrics instead when an env is still alive - approximated here by the mean over the run
@@ -57,6 +60,9 @@ def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 
         mean = obs_sum / obs_cnt
         out["obs_mean"] = mean.cpu().numpy()
         out["obs_std"] = (obs_sq / obs_cnt - mean * mean).clamp_min(0).sqrt().cpu().numpy()
+        pmean = priv_sum / obs_cnt
+        out["priv_mean"] = pmean.cpu().numpy()
+        out["priv_std"] = (priv_sq / obs_cnt - pmean * pmean).clamp_min(0).sqrt().cpu().numpy()
     return out
 
 
@@ -85,7 +91,7 @@ def main():
     net = PolicyNet((d["policy"][0][0].shape[0], *[k.shape[1] for k in d["policy"][0]]))
     net.set_params(d["policy"][0], d["policy"][1], d["mean"], d["std"])
     r = evaluate(wenv, net, episode_length=cfg.episode_length, seed=a.seed)
-    print({k: v for k, v in r.items() if not k.startswith("obs_")})
+    print({k: v for k, v in r.items() if not (k.startswith("obs_") or k.startswith("priv_"))})
 
 
 if __name__ == "__main__":
