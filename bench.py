@@ -57,7 +57,7 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--num-envs", type=int, default=4096, help="envs per GPU")
     p.add_argument("--task", default="stairs")
-    p.add_argument("--terrain", default="level1")
+    p.add_argument("--terrain", default="level1", help="level name, or 'curriculum': rank r steps on level{(r mod 10) + 1:02d} (BASELINE config[3])")
     p.add_argument("--dr", type=int, default=0, help="1 = full go2/randomize.py dynamics DR (config 3)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
@@ -200,7 +200,8 @@ def run_reference(args, cfg, table, rank):
 
 
 def workload_config(args, n_per_gpu, n_gpus):
-    return {"workload": f"GO2 joystick_pgtt {args.task} terrains/{args.terrain}.npy, {n_per_gpu} envs/GPU x {n_gpus} GPU, "
+    terr = "level01..level10 by rank (curriculum)" if getattr(args, "curriculum", False) else args.terrain
+    return {"workload": f"GO2 joystick_pgtt {args.task} terrains/{terr}.npy, {n_per_gpu} envs/GPU x {n_gpus} GPU, "
                         f"{'randomize.py on' if args.dr else 'no DR (terrain assignment only)'}, wrapped step (episode + auto-reset), 4 substeps",
             "num_envs_per_gpu": n_per_gpu, "task": args.task, "terrain": args.terrain, "dr": bool(args.dr),
             "actions": "U(-1,1), pool of 16 pre-generated device buffers", "l2": "flushed between timed steps (256 MiB write); value_l2_resident = back-to-back"}
@@ -212,8 +213,11 @@ def main():
     from phase_guided_terrain_traversal_b200 import prng, terrain
     from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
     cfg = training_overrides(default_config())
-    table = terrain.load_terrain(args.terrain) if args.task == "stairs" else None
     rank = int(os.environ.get("RANK", "0"))
+    if args.terrain == "curriculum":
+        args.curriculum = True
+        args.terrain = f"level{(rank % 10) + 1:02d}"
+    table = terrain.load_terrain(args.terrain) if args.task == "stairs" else None
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
