@@ -559,7 +559,8 @@ struct pgtt_policy {
   PolicyParams P;
   __nv_bfloat16* cw_dev;
   size_t cw_elems;
-  bool use_cluster;
+  int use_cluster;   // 1 / 0 forced by PGTT_POLICY_CLUSTER, -1 = by row count
+  int n_sm;
   __nv_bfloat16* w_dev;
   float *bias_dev, *mean_dev, *istd_dev;
   size_t w_elems, b_elems;
@@ -638,8 +639,12 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
     delete p; return pfail(PGTT_ERR_CUDA, std::string("pgtt_policy_create: ") + cudaGetErrorString(cudaGetLastError()));
   }
   P.w = p->w_dev; P.cw = p->cw_dev; P.bias = p->bias_dev; P.mean = p->mean_dev; P.inv_std = p->istd_dev;
-  p->use_cluster = true;     // PGTT_POLICY_CLUSTER=0 selects the single-CTA-per-tile kernel
+  // cluster kernel while its 4 CTAs per tile fit the SMs in one wave (<= 4736 rows on 148 SMs: 42 us vs 57 us); beyond that
+  // the single-CTA-per-tile kernel has fewer waves (8192 rows: 59 us vs ~75 us). PGTT_POLICY_CLUSTER=0|1 forces one.
+  p->use_cluster = -1;
   if (const char* e = getenv("PGTT_POLICY_CLUSTER")) p->use_cluster = atoi(e) != 0;
+  p->n_sm = 148;
+  cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
   *out = p;
   return PGTT_OK;
 }
@@ -702,7 +707,8 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
   if (!p || !obs || !action || n <= 0) return pfail(PGTT_ERR_ARG, "pgtt_policy_act: null argument or n <= 0");
   if (!p->has_params) return pfail(PGTT_ERR_STATE, "pgtt_policy_act: pgtt_policy_set_params first");
   const int blocks = (n + POL_TM - 1) / POL_TM;
-  if (p->use_cluster)
+  const bool cluster = p->use_cluster >= 0 ? p->use_cluster != 0 : blocks * POL_CL <= p->n_sm;
+  if (cluster)
     pgtt_policy_cluster_kernel<<<blocks * POL_CL, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
                                                                                           deterministic, eps, action, raw_action, log_prob, logits);
   else
