@@ -217,7 +217,11 @@ struct pgtt_env {
   bool randomized;
 };
 
-static pgtt_env* g_const_owner = nullptr;
+// The model / task constants live in __constant__ memory (one copy per device): the handle whose constants are resident is
+// tracked per device, and switching handles first drains the device so that a still-running kernel of the previous owner
+// never sees the new table.
+#define PGTT_MAX_DEVICES 64
+static pgtt_env* g_const_owner[PGTT_MAX_DEVICES] = {nullptr};
 
 static void* dev_alloc(pgtt_env* e, size_t bytes) {
   void* p = nullptr;
@@ -232,14 +236,16 @@ static void* dev_alloc(pgtt_env* e, size_t bytes) {
 }
 
 static int upload_consts(pgtt_env* e) {
-  if (g_const_owner == e) return 0;
+  const int slot = e->device >= 0 && e->device < PGTT_MAX_DEVICES ? e->device : 0;
+  if (g_const_owner[slot] == e) return 0;
 #ifndef PGTT_HOST_EMU
   CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpyToSymbol(g_mc, &e->mc, sizeof(ModelConst)));
 #else
   g_mc = e->mc;
 #endif
-  g_const_owner = e;
+  g_const_owner[slot] = e;
   return 0;
 }
 
@@ -458,7 +464,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
 
 int pgtt_destroy(pgtt_env* e) {
   if (!e) return PGTT_OK;
-  if (g_const_owner == e) g_const_owner = nullptr;
+  for (int i = 0; i < PGTT_MAX_DEVICES; i++) if (g_const_owner[i] == e) g_const_owner[i] = nullptr;
 #ifndef PGTT_HOST_EMU
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();

@@ -287,3 +287,41 @@ def test_full_size_determinism_and_shard_equivalence(train_cfg, gen):
         assert np.isfinite(full[f].astype(np.float64)).all(), f
         assert np.array_equal(full[f], again[f]), ("determinism", f)
         assert np.array_equal(full[f], np.concatenate([lo_half[f], hi_half[f]])), ("sharding", f)
+
+
+@pytest.mark.gpu
+def test_two_handles_with_different_constants_alternate(train_cfg):
+    """The constant table is one per device: handles with different task variants / models stepped alternately must each
+    reproduce their solo run bit for bit (the table is re-uploaded on every switch, after draining the device)."""
+    from phase_guided_terrain_traversal_b200.go2.configs import baseline_config, training_overrides
+    n = 64
+    keys = keys_for(n, 5)
+    rng = np.random.default_rng(0)
+    acts = [rng.uniform(-1, 1, (n, 12)).astype(np.float32) for _ in range(4)]
+    m_flat, m_st = gm.compile_model("flat_terrain"), gm.compile_model("stairs")
+    table = terr_mod.load_terrain("level07")
+
+    def make(which):
+        if which == "pgtt_stairs":
+            env = make_env("cuda", m_st, train_cfg, n)
+            env.set_terrain(table); env.randomize(keys, True)
+        else:
+            env = make_env("cuda", m_flat, training_overrides(baseline_config()), n, variant=1)
+            env.randomize(keys, True)
+        env.reset(keys + 2)
+        return env
+
+    solo = {}
+    for which in ("pgtt_stairs", "baseline_flat"):
+        env = make(which)
+        for a in acts:
+            env.step(a, wrapped=True)
+        solo[which] = (env.get("obs_state").copy(), env.get("qpos").copy())
+        env.close()
+    a_env, b_env = make("pgtt_stairs"), make("baseline_flat")
+    for a in acts:
+        a_env.step(a, wrapped=True)
+        b_env.step(a, wrapped=True)
+    for env, which in ((a_env, "pgtt_stairs"), (b_env, "baseline_flat")):
+        assert np.array_equal(env.get("obs_state"), solo[which][0]) and np.array_equal(env.get("qpos"), solo[which][1]), which
+    assert a_env.get("obs_state").shape[1] == 171 and b_env.get("obs_state").shape[1] == 162
