@@ -325,3 +325,32 @@ def test_two_handles_with_different_constants_alternate(train_cfg):
     for env, which in ((a_env, "pgtt_stairs"), (b_env, "baseline_flat")):
         assert np.array_equal(env.get("obs_state"), solo[which][0]) and np.array_equal(env.get("qpos"), solo[which][1]), which
     assert a_env.get("obs_state").shape[1] == 171 and b_env.get("obs_state").shape[1] == 162
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gen", ["warp", "quad"])
+def test_long_run_stays_finite(train_cfg, gen):
+    """1500 wrapped control steps (30 s of simulated time, random actions, level13 + DR, episodes ending and auto-resetting,
+    the 1000-step truncation included): every state field stays finite and bounded, episode bookkeeping is consistent."""
+    n, steps = 1024, 1500
+    m = gm.compile_model("stairs")
+    env = make_env("cuda-quad" if gen == "quad" else "cuda", m, train_cfg, n)
+    keys = keys_for(n, 21)
+    env.set_terrain(terr_mod.load_terrain("level13")); env.randomize(keys, True); env.reset(keys + 1)
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ndone = torch.zeros((), device="cuda")
+    ntrunc = torch.zeros((), device="cuda")
+    for s in range(steps):
+        a = torch.rand((n, 12), generator=g, device="cuda") * 2 - 1
+        env.step(a, wrapped=True)
+        ndone += env.buf["done"].sum()
+        ntrunc += env.buf["truncation"].sum()
+    for f in ("qpos", "qvel", "obs_state", "obs_privileged", "reward", "sensordata", "episode_metrics", "heightscan"):
+        x = env.get(f).astype(np.float64)
+        assert np.isfinite(x).all(), f
+    assert np.abs(env.get("qpos")[:, :2]).max() < 50 and np.abs(env.get("qvel")).max() < 200
+    assert float(ndone) > n * 0.5                      # robots under random actions fall; episodes restart
+    assert (env.get("steps")[:, 0] <= 1000).all() and (env.get("step")[:, 0] == steps).all()
+    q = env.get("qpos")[:, 3:7]
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-4
