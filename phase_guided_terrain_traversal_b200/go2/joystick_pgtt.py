@@ -78,5 +78,13 @@ class Joystick(Go2Env):
                                         "box_friction", "floor_friction", "terrain_index")}
 
     # -- go2/joystick_pgtt.py:603-611 (host restatement for inspection; the kernel samples in-place) --------
-    def sample_command(self, rng, x):
-        raise NotImplementedError("commands are resampled inside the fused step kernel (csrc/pgtt_env.cuh:env_step)")
+    def sample_command(self, rng, x_k):
+        """Host restatement for a single env (numpy, bit-compatible with jax.random); inside `step` the fused kernel
+        resamples in place (csrc/pgtt_env.cuh:env_step). rng: uint32[2], x_k: float[3] -> float32[3]."""
+        part = self._rng_partitionable
+        _, y_rng, w_rng, z_rng = prng.split(np.asarray(rng, dtype=np.uint32), 4, part)
+        y_k = prng.uniform(y_rng, (3,), self._cmd_u_min, self._cmd_u_max, part)
+        z_k = prng.bernoulli(z_rng, self._cmd_b, (3,), part).astype(np.float32)
+        w_k = prng.bernoulli(w_rng, 0.5, (3,), part).astype(np.float32)
+        x_k = np.asarray(x_k, dtype=np.float32)
+        return (x_k - w_k * (x_k - y_k * z_k)).astype(np.float32)

@@ -444,8 +444,16 @@ def extra_vectors(out_dir):
     q = g.normal(size=(64, 4)).astype(np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)
     yaw = np.array([np.float32(ref_yaw(J(qq))) for qq in q], np.float32)
+    # Joystick.sample_command (go2/joystick_pgtt.py:603-611) of the reference class on 32 keys
+    from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
+    cfg = training_overrides(default_config())
+    ref_env = make_reference_env("flat_terrain", cfg, gm.compile_model("flat_terrain"), STATE)
+    ckeys = prng.env_keys(77, 32)
+    cx = g.uniform(-1, 1, (32, 3)).astype(np.float32)
+    cmd = np.stack([np.asarray(ref_env.sample_command(ckeys[i], J(cx[i])), np.float32) for i in range(32)])
     np.savez_compressed(Path(out_dir) / "closed_form.npz", phi=phi, swing_heights=hs, get_z=z.astype(np.float32), quat=q, yaw=yaw,
-                        phases=np.asarray(ref_gait.PHASES, np.float32), p_stance=np.float32(ref_gait.p_stance))
+                        phases=np.asarray(ref_gait.PHASES, np.float32), p_stance=np.float32(ref_gait.p_stance),
+                        cmd_keys=ckeys, cmd_x=cx, cmd_out=cmd)
     print("wrote closed_form.npz")
     # the reference's config factories, evaluated (go2/configs.py:6-152) and its constants (go2/go2_constants.py)
     import json

@@ -189,3 +189,13 @@ def _compare_loose(get, g, tag, seed_tag, who):
     for k in ("step", "steps_until_next_cmd", "last_contact", "rng", "last_act", "last_last_act"):
         assert np.array_equal(np.asarray(get(INFO_MAP[k][0], INFO_MAP[k][1]), np.float64).reshape(-1),
                               np.asarray(g[p + "info/" + k], np.float64).reshape(-1)), (who, seed_tag, tag, k)
+
+
+def test_sample_command_matches_reference_method():
+    """Host `Joystick.sample_command` against the reference method evaluated by make_golden.py (32 keys)."""
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    g = np.load(GOLD / "closed_form.npz")
+    env = Joystick(task="flat_terrain", config=_cfg())
+    out = np.stack([env.sample_command(k, x) for k, x in zip(g["cmd_keys"], g["cmd_x"])])
+    assert np.array_equal(out, g["cmd_out"])
+    assert (out != g["cmd_x"]).any() and (out == g["cmd_x"]).any()      # both branches of the w_k coin occur
