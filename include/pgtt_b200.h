@@ -184,7 +184,9 @@ int pgtt_record(pgtt_env* env, float* obs_state_dst, float* obs_priv_dst, float*
  * launches issued natively on `stream` (3 kernels per control step, nothing returns to the host in between).
  * Buffers are DEVICE, time-major: obs_* [T + 1][N][dim] (slot 0 = the observation the unroll starts from, so
  * next_observation[t] = observation[t + 1]); action / raw_action [T][N][12]; log_prob / reward / discount /
- * truncation [T][N]. Internal exploration noise is keyed by (seed, step0 + t). */
+ * truncation [T][N]. Internal exploration noise is keyed by (seed, step0 + t). The 1 + 3 T launches are captured into a
+ * CUDA graph on first use (per env / buffers / T) and replayed on an internal stream ordered after and before the
+ * caller's stream (PGTT_ROLLOUT_GRAPH=0 issues them directly). */
 typedef struct {
   float *obs_state, *obs_privileged, *action, *raw_action, *log_prob, *reward, *discount, *truncation;
 } pgtt_rollout_buffers;

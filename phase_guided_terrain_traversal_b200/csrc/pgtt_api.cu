@@ -614,6 +614,8 @@ int pgtt_obs_dims(pgtt_env* e, int* nobs, int* npriv) {
   return PGTT_OK;
 }
 int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
+// graph replays of the rollout launch this handle's kernels without going through launch(): keep the counter honest
+void pgtt_internal_count_launches(pgtt_env* e, int64_t n) { if (e) e->launches += n; }
 
 int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* tr, void* stream) {
   if (!e) return fail(PGTT_ERR_ARG, "pgtt_record: null handle");

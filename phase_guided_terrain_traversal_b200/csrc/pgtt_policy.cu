@@ -28,6 +28,8 @@
 
 #include "../../include/pgtt_b200.h"
 
+extern "C" void pgtt_internal_count_launches(pgtt_env* env, int64_t n);   // pgtt_api.cu (not part of the ABI header)
+
 #define POL_TM 128            // envs per CTA = MMA M
 #define POL_MAXK 512          // widest activation
 #define POL_MAXLAYERS 6
@@ -179,10 +181,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // are recycled on the tcgen05.commit of the MMAs that read them) and the MMA issuer. full[b] / empty[b]: chunk g uses
 // buffer b = g & 1 and completion number g >> 1 of both barriers.
 __global__ void __launch_bounds__(POL_THREADS, 1)
-pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step,
-                   int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
+pgtt_policy_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step_in,
+                   const unsigned long long* __restrict__ step_base, int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
                    float* __restrict__ log_prob, float* __restrict__ logits_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const unsigned long long step = step_in + (step_base ? *step_base : 0ull);   // noise counter; the base lives on the device for graph replays
   uint8_t* sA = smem;
   uint8_t* sB = smem + POL_A_BYTES;                                                  // [POL_NBUF][POL_BCHUNK]
   float* sBias = reinterpret_cast<float*>(smem + POL_A_BYTES + POL_NBUF * POL_BCHUNK);
@@ -372,10 +375,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cta_addr, uint32_t rank, 
 }
 
 __global__ void __cluster_dims__(POL_CL, 1, 1) __launch_bounds__(POL_THREADS, 1)
-pgtt_policy_cluster_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step,
-                           int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
+pgtt_policy_cluster_kernel(PolicyParams P, const float* __restrict__ obs, int n_rows, unsigned long long seed, unsigned long long step_in,
+                           const unsigned long long* __restrict__ step_base, int deterministic, const float* __restrict__ eps_in, float* __restrict__ action, float* __restrict__ raw_action,
                            float* __restrict__ log_prob, float* __restrict__ logits_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const unsigned long long step = step_in + (step_base ? *step_base : 0ull);   // noise counter; the base lives on the device for graph replays
   uint8_t* sA = smem;
   uint8_t* sB = smem + POL_A_BYTES;
   float* sBias = reinterpret_cast<float*>(smem + POL_A_BYTES + POL_NBUF * POL_BCHUNK);
@@ -561,6 +565,14 @@ struct pgtt_policy {
   size_t cw_elems;
   int use_cluster;   // 1 / 0 forced by PGTT_POLICY_CLUSTER, -1 = by row count
   int n_sm;
+  // rollout graph: the T-step unroll (1 + 3 T launches) captured once per (env, buffers, T, deterministic) and replayed
+  const unsigned long long* step_base_arg;   // what pgtt_policy_act passes to the kernels (NULL outside a rollout graph)
+  unsigned long long* step_dev;              // device-side noise counter base of the graph
+  cudaStream_t gstream;
+  cudaEvent_t ev_in, ev_out;
+  cudaGraphExec_t gexec;
+  struct { pgtt_env* env; int T, deterministic; uint64_t seed; pgtt_rollout_buffers o; } gkey;
+  int use_graph;
   __nv_bfloat16* w_dev;
   float *bias_dev, *mean_dev, *istd_dev;
   size_t w_elems, b_elems;
@@ -645,6 +657,10 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
   if (const char* e = getenv("PGTT_POLICY_CLUSTER")) p->use_cluster = atoi(e) != 0;
   p->n_sm = 148;
   cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
+  p->step_base_arg = nullptr; p->step_dev = nullptr; p->gstream = nullptr; p->ev_in = p->ev_out = nullptr; p->gexec = nullptr;
+  memset(&p->gkey, 0, sizeof(p->gkey));
+  p->use_graph = 1;
+  if (const char* e = getenv("PGTT_ROLLOUT_GRAPH")) p->use_graph = atoi(e) != 0;
   *out = p;
   return PGTT_OK;
 }
@@ -652,6 +668,11 @@ int pgtt_policy_create(int device, const int* sizes, int n_layers, pgtt_policy**
 int pgtt_policy_destroy(pgtt_policy* p) {
   if (!p) return PGTT_OK;
   cudaSetDevice(p->device); cudaDeviceSynchronize();
+  if (p->gexec) cudaGraphExecDestroy(p->gexec);
+  if (p->gstream) cudaStreamDestroy(p->gstream);
+  if (p->ev_in) cudaEventDestroy(p->ev_in);
+  if (p->ev_out) cudaEventDestroy(p->ev_out);
+  cudaFree(p->step_dev);
   cudaFree(p->cw_dev); cudaFree(p->w_dev); cudaFree(p->bias_dev); cudaFree(p->mean_dev); cudaFree(p->istd_dev);
   delete p;
   return PGTT_OK;
@@ -710,10 +731,10 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
   const bool cluster = p->use_cluster >= 0 ? p->use_cluster != 0 : blocks * POL_CL <= p->n_sm;
   if (cluster)
     pgtt_policy_cluster_kernel<<<blocks * POL_CL, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
-                                                                                          deterministic, eps, action, raw_action, log_prob, logits);
+                                                                                          p->step_base_arg, deterministic, eps, action, raw_action, log_prob, logits);
   else
     pgtt_policy_kernel<<<blocks, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(p->P, obs, n, (unsigned long long)seed, (unsigned long long)step,
-                                                                          deterministic, eps, action, raw_action, log_prob, logits);
+                                                                          p->step_base_arg, deterministic, eps, action, raw_action, log_prob, logits);
   PCUDA(cudaGetLastError());
   p->launches++;
   return PGTT_OK;
@@ -818,15 +839,9 @@ int pgtt_ppo_head(const float* logits, const float* baseline, const float* raw_a
 }
 
 // generate_unroll: T x (act -> wrapped step -> record); see include/pgtt_b200.h
-int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t step0, int deterministic, const pgtt_rollout_buffers* o, void* stream) {
-  if (!env || !pol || !o || T <= 0) return pfail(PGTT_ERR_ARG, "pgtt_rollout: null argument or T <= 0");
-  if (!o->obs_state || !o->action) return pfail(PGTT_ERR_ARG, "pgtt_rollout: obs_state and action buffers are required");
-  pgtt_buffers b;
-  if (int rc = pgtt_get_buffers(env, &b)) return pfail(rc, pgtt_last_error());
-  const size_t N = (size_t)b.num_envs, A = (size_t)pol->P.act_dim;
-  int nobs = 0, npriv = 0;
-  pgtt_obs_dims(env, &nobs, &npriv);
-  if (pol->P.obs_dim != nobs || A != PGTT_NU) return pfail(PGTT_ERR_ARG, "pgtt_rollout: policy must map the env's obs[\"state\"] (171 or 162) -> 2 x 12 logits");
+static int rollout_issue(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t step0, int deterministic, const pgtt_rollout_buffers* o,
+                         size_t N, int nobs, int npriv, void* stream) {
+  const size_t A = (size_t)pol->P.act_dim;
   // slot 0: the observation the unroll starts from; reward / discount / truncation slots are only written after a step
   if (int rc = pgtt_record(env, o->obs_state, o->obs_privileged, nullptr, nullptr, nullptr, stream)) return pfail(rc, pgtt_last_error());
   for (int t = 0; t < T; t++) {
@@ -840,6 +855,65 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t
                              o->reward ? o->reward + (size_t)t * N : nullptr, o->discount ? o->discount + (size_t)t * N : nullptr,
                              o->truncation ? o->truncation + (size_t)t * N : nullptr, stream)) return pfail(rc, pgtt_last_error());
   }
+  return PGTT_OK;
+}
+
+__global__ void pgtt_set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t step0, int deterministic, const pgtt_rollout_buffers* o, void* stream) {
+  if (!env || !pol || !o || T <= 0) return pfail(PGTT_ERR_ARG, "pgtt_rollout: null argument or T <= 0");
+  if (!o->obs_state || !o->action) return pfail(PGTT_ERR_ARG, "pgtt_rollout: obs_state and action buffers are required");
+  pgtt_buffers b;
+  if (int rc = pgtt_get_buffers(env, &b)) return pfail(rc, pgtt_last_error());
+  const size_t N = (size_t)b.num_envs;
+  int nobs = 0, npriv = 0;
+  pgtt_obs_dims(env, &nobs, &npriv);
+  if (pol->P.obs_dim != nobs || pol->P.act_dim != PGTT_NU) return pfail(PGTT_ERR_ARG, "pgtt_rollout: policy must map the env's obs[\"state\"] (171 or 162) -> 2 x 12 logits");
+  if (!pol->use_graph) return rollout_issue(env, pol, T, seed, step0, deterministic, o, N, nobs, npriv, stream);
+
+  // CUDA-graph path: the unroll is captured once on an internal stream (the caller's stream may be the legacy default
+  // stream, which cannot be captured) and replayed; the exploration-noise counter base lives on the device.
+  cudaStream_t user = (cudaStream_t)stream;
+  if (!pol->gstream) {
+    PCUDA(cudaStreamCreateWithFlags(&pol->gstream, cudaStreamNonBlocking));
+    PCUDA(cudaEventCreateWithFlags(&pol->ev_in, cudaEventDisableTiming));
+    PCUDA(cudaEventCreateWithFlags(&pol->ev_out, cudaEventDisableTiming));
+    PCUDA(cudaMalloc(&pol->step_dev, sizeof(unsigned long long)));
+  }
+  const bool same = pol->gexec && pol->gkey.env == env && pol->gkey.T == T && pol->gkey.deterministic == deterministic && pol->gkey.seed == seed &&
+                    memcmp(&pol->gkey.o, o, sizeof(*o)) == 0;
+  if (!same) {
+    if (pol->gexec) { cudaGraphExecDestroy(pol->gexec); pol->gexec = nullptr; }
+    // make sure this env's constant table is resident before capturing (an upload synchronises the device)
+    if (int rc = pgtt_record(env, nullptr, nullptr, nullptr, nullptr, nullptr, user)) return pfail(rc, pgtt_last_error());
+    PCUDA(cudaStreamSynchronize(user));
+    cudaGraph_t graph = nullptr;
+    pol->step_base_arg = pol->step_dev;
+    cudaError_t ce = cudaStreamBeginCapture(pol->gstream, cudaStreamCaptureModeThreadLocal);
+    int rc = PGTT_OK;
+    if (ce == cudaSuccess) {
+      rc = rollout_issue(env, pol, T, seed, 0, deterministic, o, N, nobs, npriv, pol->gstream);
+      ce = cudaStreamEndCapture(pol->gstream, &graph);
+    }
+    pol->step_base_arg = nullptr;
+    if (ce == cudaSuccess && rc == PGTT_OK && graph) ce = cudaGraphInstantiate(&pol->gexec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || rc != PGTT_OK || !pol->gexec) {   // no graph: issue directly (and stop trying)
+      cudaGetLastError();
+      pol->gexec = nullptr; pol->use_graph = 0;
+      return rollout_issue(env, pol, T, seed, step0, deterministic, o, N, nobs, npriv, stream);
+    }
+    pol->gkey.env = env; pol->gkey.T = T; pol->gkey.deterministic = deterministic; pol->gkey.seed = seed; pol->gkey.o = *o;
+  } else {
+    pgtt_internal_count_launches(env, 1 + 2 * (int64_t)T);   // capture counted the first unroll's launches
+    pol->launches += T;
+  }
+  PCUDA(cudaEventRecord(pol->ev_in, user));
+  PCUDA(cudaStreamWaitEvent(pol->gstream, pol->ev_in, 0));
+  pgtt_set_u64_kernel<<<1, 1, 0, pol->gstream>>>(pol->step_dev, (unsigned long long)step0);
+  PCUDA(cudaGraphLaunch(pol->gexec, pol->gstream));
+  PCUDA(cudaEventRecord(pol->ev_out, pol->gstream));
+  PCUDA(cudaStreamWaitEvent(user, pol->ev_out, 0));
   return PGTT_OK;
 }
 
