@@ -491,8 +491,48 @@ def policy_vectors(out_dir):
     print("wrote policy177.npz")
 
 
+def terrain_vectors(out_dir):
+    """terrain/generator.py + terrain/getIndexes.py of the reference, imported unmodified (cv2 / noise / alive_progress / jax are
+    only imported at module level there and get empty stand-ins): the 14-tile adjacency tables `generate_14` hands to the WFC
+    solver, and the boxes `addElement` creates for every tile kind at three (width, step height, steps) settings."""
+    import json
+    import os
+    for name in ("cv2", "noise", "alive_progress"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["alive_progress"].alive_bar = lambda *a, **k: None
+    sys.modules["alive_progress"].alive_it = lambda x: x
+    sys.path.insert(0, str(REF / "terrain"))
+    sys.path.insert(0, str(REF))
+    cwd = os.getcwd()
+    os.chdir(REF)                 # the generator parses ./go2/xmls/scene_mjx_feetonly.xml in its constructor
+    try:
+        import generator as ref_gen
+        import getIndexes as ref_idx
+        left, right, up, down = (-1, 0), (1, 0), (0, 1), (0, -1)
+        directions = [left, down, right, up]
+        conn = {0: {left: (0, 4, 10, 11), down: (0, 5, 11, 12), right: (0, 2, 12, 13), up: (0, 3, 13, 10)},      # generator.py:295-298
+                1: {left: (1, 2, 6, 7), down: (1, 3, 7, 8), right: (1, 4, 8, 9), up: (1, 5, 9, 6)}}
+        conn.update(ref_idx.Stairs(directions)); conn.update(ref_idx.StairsTurningUp(directions)); conn.update(ref_idx.StairsTurningDown(directions))
+        table = {str(t): {f"{d[0]},{d[1]}": sorted(int(x) for x in v) for d, v in per.items()} for t, per in conn.items()}
+        (Path(out_dir) / "terrain_adjacency.json").write_text(json.dumps(table, indent=1, sort_keys=True))
+        out = {}
+        settings = [(0.3, 0.07, 2), (0.41, 0.13, 3), (0.45, 0.04, 4)]
+        out["settings"] = np.array(settings)
+        for si, (w, h, n) in enumerate(settings):
+            for tile in range(14):
+                tgen = ref_gen.TerrainGenerator(width=w, step_height=h, num_stairs=n, render=False)
+                ref_gen.addElement(tgen, tile, [0.7, -1.1])
+                rows = [np.concatenate([b["pos"], b["quat"], b["size"]]) for b in tgen.box_data]
+                out[f"s{si}_tile{tile}"] = np.array(rows, np.float64).reshape(-1, 10)
+        np.savez_compressed(Path(out_dir) / "terrain_tiles.npz", **out)
+    finally:
+        os.chdir(cwd)
+    print("wrote terrain_adjacency.json, terrain_tiles.npz")
+
+
 if __name__ == "__main__":
     out_dir = Path(__file__).resolve().parent
+    terrain_vectors(out_dir)
     policy_vectors(out_dir)
     extra_vectors(out_dir)
     run_case("flat", "flat_terrain", None, dr=1, seeds=[0, 1], n_steps=12, out_dir=out_dir)
