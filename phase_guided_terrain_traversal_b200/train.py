@@ -44,7 +44,8 @@ def run_training(args):
         registry._randomizer[env_name] = randomize_simple.domain_randomize
     cfg = ppo.PPOConfig(num_timesteps=args.num_timesteps, episode_length=env_cfg.episode_length, num_minibatches=args.num_minibatches,
                         discounting=args.discount, learning_rate=args.learning_rate, num_envs=args.num_envs, batch_size=args.batch_size,
-                        seed=args.seed, matmul_precision=args.matmul_precision)                                                                                # train.py:135-161
+                        seed=args.seed, matmul_precision=args.matmul_precision,
+                        global_advantage_norm=bool(args.global_advantage_norm))                                                                                # train.py:135-161
     keys = sharding.shard_keys(args.seed, args.num_envs, rank, world)
     t0 = time.time()
 
@@ -76,6 +77,8 @@ def main():
     p.add_argument("--num_timesteps", type=int, default=1)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--out", type=str, default=None)
+    p.add_argument("--global_advantage_norm", type=int, default=1,
+                   help="1: advantages normalised with moments all-reduced over all ranks (NCCL; the north-star variant), 0: per-rank minibatch (brax)")
     p.add_argument("--matmul_precision", type=str, default="highest", help="learner GEMMs: highest (fp32, reference) or high (TF32)")
     args = p.parse_args()
     if args.method not in ("pgtt", "baseline"):
