@@ -41,7 +41,8 @@ def allreduce_moments(x, group=None):
     import torch.distributed as dist
     feat = x.shape[1:]
     xf = x.reshape(x.shape[0], -1).to(torch.float64)
-    packed = torch.cat([torch.tensor([float(x.shape[0])], dtype=torch.float64, device=x.device), xf.sum(0), (xf * xf).sum(0)])
+    # (torch.full, not torch.tensor: no host-to-device copy, so the reduction can sit inside a CUDA-graph capture)
+    packed = torch.cat([torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=x.device), xf.sum(0), (xf * xf).sum(0)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
     d = xf.shape[1]

@@ -60,6 +60,12 @@ def run_training(args):
         trainer.save(args.out)                                                                                       # model.save_params, train.py:266
         print(f"saved {args.out} (layout of deploy/policy_net.py:6-33)")
     if world > 1:
+        # a captured graph that contains NCCL kernels must be gone before its communicator is torn down
+        trainer._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
     return trainer
 
