@@ -1016,6 +1016,9 @@ void orc_task_step(const TaskCfg* t, Env* e, const real* action) {
   quadrant_stats(t, in);
   get_obs(t, e);
   int done = s[24] < 0; /* upvector z */
+  /* failure guard shared with the kernels (not in the reference): a non-finite or absurd state ends the episode */
+  for (int i = 0; i < NQ; i++) if (!(FABS(d->qpos[i]) < (real)1e6)) done = 1;
+  for (int i = 0; i < NV; i++) if (!(FABS(d->qvel[i]) < (real)1e6)) done = 1;
   /* rewards, in the dict order of _get_reward (joystick_pgtt.py:382-420) */
   const real* cmd = in->command; const real* q = d->qpos + 7; const real* qd = d->qvel + 6; const real* af = d->actuator_force;
   real cmd_norm = SQRT(dot3(cmd, cmd));

@@ -303,7 +303,13 @@ DEV void env_step(WS& w, const EnvBuffers& B, const float* action_all, int env, 
     write_obs(w, B, env, rng, sc, B.gait_freq[env], la, w.tb, sci, sc + 4, lane);
     update_history(w, B, env, step, B.motor_targets + (size_t)env * NU, lane);
   }
-  const int done = w.sens[24] < 0.f;
+  // termination (joystick_pgtt.py:233-236) + a failure guard the reference does not have: a non-finite or
+  // absurd generalised state ends the episode, so the auto-reset wrapper restores the env instead of carrying NaNs forever
+  bool bad = false;
+  if (lane < NQ) bad = !(fabsf(w.qpos[lane]) < 1e6f);
+  if (lane < NV) bad |= !(fabsf(w.qvel[lane]) < 1e6f);
+  const bool poisoned = any_lane(bad);
+  const int done = (w.sens[24] < 0.f) || poisoned;
   // rewards (joystick_pgtt.py:372-599); lanes 0..3 hold per-foot partials, lanes 0..11 per-joint partials
   const float* sdat = w.sens;
   const float cmd0 = w.tb[0], cmd1 = w.tb[1], cmd2 = w.tb[2];

@@ -1511,7 +1511,16 @@ DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, i
       qv[i] = X.vl[t]; qe[i] = X.ql[t] - mtA[t];
     }
   }
-  const int done = Z.up[2] < 0.f;
+  // termination (joystick_pgtt.py:233-236) + failure guard (see pgtt_env.cuh:env_step): non-finite / absurd state ends the episode
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 7; i++) bad |= !(fabsf(X.qb[i]) < 1e6f);
+#pragma unroll
+  for (int i = 0; i < 6; i++) bad |= !(fabsf(X.vb[i]) < 1e6f);
+#pragma unroll
+  for (int t = 0; t < 3; t++) bad |= !(fabsf(X.ql[t]) < 1e6f) || !(fabsf(X.vl[t]) < 1e6f);
+  const bool poisoned = qany(bad, qbase);   // collective: every lane takes part
+  const int done = (Z.up[2] < 0.f) || poisoned;
   // rewards (joystick_pgtt.py:372-599): per-joint / per-foot partials on the owning lane, summed over the quad
   const float cmd_norm = sqrtf(cmd0 * cmd0 + cmd1 * cmd1 + cmd2 * cmd2);
   float vals[15];

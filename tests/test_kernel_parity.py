@@ -354,3 +354,20 @@ def test_long_run_stays_finite(train_cfg, gen):
     assert (env.get("steps")[:, 0] <= 1000).all() and (env.get("step")[:, 0] == steps).all()
     q = env.get("qpos")[:, 3:7]
     assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-4
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_non_finite_state_ends_the_episode(kind, train_cfg):
+    """Failure guard (not in the reference where NaNs propagate silently): envs whose state is poisoned are
+    terminated and restored from their first state by the auto-reset wrapper; healthy envs are untouched."""
+    m, orc, env, keys = setup_pair(kind, "flat_terrain", train_cfg, dyn=False)
+    orc.reset(keys); env.reset(keys)
+    first_q = env.get("qpos").copy()
+    q = orc.get("qvel"); q[3, 7] = np.nan; q[5, 2] = np.inf
+    orc.set("qvel", q); env.set("qvel", q.astype(np.float32))
+    act = np.zeros((N, 12), np.float32)
+    orc.step(act.astype(np.float64)); env.step(act)
+    d = env.get("done")[:, 0]
+    assert d[3] == 1 and d[5] == 1 and d.sum() == 2 and np.array_equal(d, orc.get("done")[:, 0])
+    assert np.array_equal(env.get("qpos")[[3, 5]], first_q[[3, 5]]) and np.isfinite(env.get("qpos")).all()
+    assert np.isfinite(env.get("reward")).all() and np.isfinite(env.get("obs_state")).all()
