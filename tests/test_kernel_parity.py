@@ -45,11 +45,11 @@ def random_states(m, n, seed):
     return qpos, qvel, ctrl, warm
 
 
-def setup_pair(kind, task, cfg, dyn=True, part=True, seed_hi=7, level="level07"):
+def setup_pair(kind, task, cfg, dyn=True, part=True, seed_hi=7, level="level07", n=N):
     m = gm.compile_model(task)
-    orc = Oracle(m, cfg, N, "f32", rng_partitionable=part)
-    env = make_env(kind, m, cfg, N, rng_partitionable=part)
-    keys = keys_for(N, seed_hi)
+    orc = Oracle(m, cfg, n, "f32", rng_partitionable=part)
+    env = make_env(kind, m, cfg, n, rng_partitionable=part)
+    keys = keys_for(n, seed_hi)
     if task == "stairs":
         table = terr_mod.load_terrain(level)
         orc.randomize(keys, table, dyn); env.set_terrain(table); env.randomize(keys, dyn)
@@ -371,3 +371,18 @@ def test_non_finite_state_ends_the_episode(kind, train_cfg):
     assert d[3] == 1 and d[5] == 1 and d.sum() == 2 and np.array_equal(d, orc.get("done")[:, 0])
     assert np.array_equal(env.get("qpos")[[3, 5]], first_q[[3, 5]]) and np.isfinite(env.get("qpos")).all()
     assert np.isfinite(env.get("reward")).all() and np.isfinite(env.get("obs_state")).all()
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+@pytest.mark.parametrize("n", [1, 13])
+def test_single_and_ragged_env_counts(kind, n, train_cfg):
+    """BASELINE config[0] (one env) and an env count that fills neither a warp of the quad kernel (8 envs) nor a CTA of the
+    warp-per-env kernel (14 envs): the idle lanes / warps take part in every collective and write nothing."""
+    m, orc, env, keys = setup_pair(kind, "stairs" if n > 1 else "flat_terrain", train_cfg, dyn=True, n=n)
+    orc.reset(keys + 11); env.reset(keys + 11)
+    compare_state(orc, env, "reset")
+    rng = np.random.default_rng(n)
+    for s in range(3):
+        act = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        orc.step(act.astype(np.float64)); env.step(act)
+        compare_state(orc, env, f"n={n} step{s}")
