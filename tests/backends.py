@@ -8,7 +8,8 @@ import pytest
 
 def make_env(kind, model, cfg, n, **kw):
     base, _, gen = kind.partition("-")
-    os.environ["PGTT_KERNEL"] = "quad" if gen.startswith("quad") else "warp"
+    if gen != "auto":   # "cuda-auto": the generation pgtt_create picks from the env count
+        os.environ["PGTT_KERNEL"] = "quad" if gen.startswith("quad") else "warp"
     os.environ["PGTT_QUAD_FULLSCAN"] = "1" if gen == "quadfull" else "0"
     try:
         if base == "emu":
