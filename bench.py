@@ -56,6 +56,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--num-envs", type=int, default=4096, help="envs per GPU")
+    p.add_argument("--total-envs", type=int, default=0, help="strong-scaling mode: this many envs in total, split by index over the ranks (sharding.shard); overrides --num-envs")
     p.add_argument("--task", default="stairs")
     p.add_argument("--terrain", default="level1", help="level name, or 'curriculum': rank r steps on level{(r mod 10) + 1:02d} (BASELINE config[3])")
     p.add_argument("--dr", type=int, default=0, help="1 = full go2/randomize.py dynamics DR (config 3)")
@@ -238,8 +239,12 @@ def main():
     from phase_guided_terrain_traversal_b200.go2 import randomize, randomize_simple
     from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
 
-    N = args.num_envs
-    keys = prng.env_keys(0, N, offset=rank * N)
+    N, offset = args.num_envs, rank * args.num_envs
+    if args.total_envs:
+        from phase_guided_terrain_traversal_b200 import sharding
+        offset, stop = sharding.shard(args.total_envs, rank, world)
+        N = stop - offset
+    keys = prng.env_keys(0, N, offset=offset)
     env = Joystick(task=args.task, config=cfg, device=local_rank)
     if args.task == "stairs":
         rfn = functools.partial(randomize.domain_randomize, rng=keys, terrain_matrix=table, dynamics=bool(args.dr))
@@ -344,12 +349,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        total_envs = N * world
+        total_envs = args.total_envs if args.total_envs else N * world
         value = total_envs * K / (ms_cold * 1e-3)
         achieved = B_ALG * N / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_cold / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.total_envs else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, N, world),
             "value_l2_resident": total_envs * K / (ms_resident * 1e-3), "ms_per_step_l2_resident": ms_resident / K,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * 12 * 4, "d2h_bytes_per_step": N * 2 * 4,
