@@ -13,6 +13,7 @@ step, observation statistics and (optionally) advantage moments with `sharding.a
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence
@@ -48,6 +49,7 @@ class PPOConfig:                      # names and defaults of training/train.py:
     seed: int = 0
     use_cuda_graph: bool = True
     fused_head: bool = True               # PPO loss head + its gradients from the hand-written kernel `pgtt_ppo_head`
+    parallel_nets: bool = True            # value network (forward and backward) on a second CUDA stream beside the policy network
     # learner GEMM precision: "highest" = fp32 like the reference (jax_default_matmul_precision=highest, train.py:94),
     # "high" = TF32 tensor cores (fp32 storage and accumulation, 10-bit mantissa products)
     matmul_precision: str = "highest"
@@ -91,11 +93,16 @@ def compute_gae_native(truncation, discount, rewards, values_all, lambda_: float
 
 
 _LINEAR = None
+_ONES: Dict = {}
+_SCALARS = ("log_prob", "reward", "discount", "truncation")
 
 
 def _linear():
-    """Dense layer whose backward computes the bias gradient as a (1 x M) @ (M x N) GEMM: torch's column reduction takes
-    18 us per layer on [5120, 512] (15 % of the SGD step, profiles/r01c_learner_launches.csv), the GEMM ~4 us."""
+    """Dense layer with a hand-arranged backward (profiles/r01c_learner_launches.csv, tools/learner_profile.py):
+    * the bias gradient is a (1 x M) @ (M x N) GEMM: torch's column reduction takes 18 us per layer on [5120, 512], the GEMM ~4 us;
+    * no input gradient is formed for a layer whose input does not need one (the first layer: a [5120, 512] @ [512, 171] GEMM);
+    * the input may carry zero-padded trailing columns (171 -> 172, 215 -> 216): K is then a multiple of four and the
+      weight-gradient GEMM takes the aligned tensor-core path (57 -> ~10 us); the kernel is padded with zero rows on the fly."""
     global _LINEAR
     if _LINEAR is None:
         import torch
@@ -103,16 +110,30 @@ def _linear():
         class Linear(torch.autograd.Function):
             @staticmethod
             def forward(ctx, x, k, b):
-                ctx.save_for_backward(x, k)
-                return torch.addmm(b, x, k)
+                pad = x.shape[1] - k.shape[0]
+                kp = torch.nn.functional.pad(k, (0, 0, 0, pad)) if pad else k
+                ctx.save_for_backward(x, kp)
+                ctx.rows = k.shape[0]
+                return torch.addmm(b, x, kp)
 
             @staticmethod
             def backward(ctx, g):
-                x, k = ctx.saved_tensors
-                ones = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)
-                return g @ k.t(), x.t() @ g, (ones @ g).reshape(-1)
+                x, kp = ctx.saved_tensors
+                key = (g.shape[0], g.device, g.dtype)
+                ones = _ONES.get(key)
+                if ones is None:
+                    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                        ones = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)     # (not cached: graph-pool memory)
+                    else:
+                        ones = _ONES[key] = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)
+                gx = g @ kp.t() if ctx.needs_input_grad[0] else None
+                return gx, (x.t() @ g)[:ctx.rows], (ones @ g).reshape(-1)
         _LINEAR = Linear
     return _LINEAR
+
+
+def pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
 
 
 def mlp(x, kernels, biases):
@@ -179,15 +200,28 @@ def _fused_head():
     return PPOHead
 
 
-def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_fn: Optional[Callable] = None, fused: bool = False):
+def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_fn: Optional[Callable] = None, fused: bool = False,
+             side_stream=None):
     """batch: time-major [T, B, ...] tensors with NORMALISED observations `obs`, `obs_priv` ([T + 1, B, .]) plus
-    raw_action, log_prob, reward, discount, truncation ([T, B]) and entropy noise `eps` [T, B, A]."""
+    raw_action, log_prob, reward, discount, truncation ([T, B]) and entropy noise `eps` [T, B, A].
+    `side_stream`: the value network runs there, concurrently with the policy network (autograd replays each backward on
+    its forward's stream, so the two backward chains overlap as well); both are captured into the SGD-step graph as
+    parallel branches."""
     import torch
     pk, pb = policy_params
     vk, vb = value_params
     T = batch["reward"].shape[0]
-    logits = mlp(batch["obs"][:T], pk, pb)
-    baseline_all = mlp(batch["obs_priv"], vk, vb).squeeze(-1)           # [T + 1, B]
+    if side_stream is not None:
+        cur = torch.cuda.current_stream(batch["obs"].device)
+        side_stream.wait_stream(cur)
+        with torch.cuda.stream(side_stream):
+            baseline_all = mlp(batch["obs_priv"], vk, vb).squeeze(-1)   # [T + 1, B]
+        logits = mlp(batch["obs"][:T], pk, pb)
+        cur.wait_stream(side_stream)
+        baseline_all.record_stream(cur)
+    else:
+        logits = mlp(batch["obs"][:T], pk, pb)
+        baseline_all = mlp(batch["obs_priv"], vk, vb).squeeze(-1)       # [T + 1, B]
     baseline, bootstrap = baseline_all[:T], baseline_all[T]
     rewards = batch["reward"] * cfg.reward_scaling
     truncation = batch["truncation"]
@@ -294,6 +328,7 @@ class PPOTrainer:
         self.gen.manual_seed(cfg.seed * 31 + 1 + self.rank)
         self.env_steps = 0
         self._graph = None
+        self._side = None
         self._data: Dict = {}
         self.metrics: Dict = {}
         self._sync_policy()
@@ -315,8 +350,11 @@ class PPOTrainer:
 
     def _sgd_body(self, batch):
         torch = self.torch
-        loss, m = ppo_loss(self.policy_params, self.value_params, batch, self.cfg, self._moments, fused=self.cfg.fused_head)
-        self.opt.zero_grad(set_to_none=False)
+        if self.cfg.parallel_nets and self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        loss, m = ppo_loss(self.policy_params, self.value_params, batch, self.cfg, self._moments, fused=self.cfg.fused_head,
+                           side_stream=self._side if self.cfg.parallel_nets else None)
+        self.opt.zero_grad(set_to_none=True)    # backward writes fresh gradients: no fill + accumulate pair per parameter
         loss.backward()
         if self.world > 1:
             flat = torch.cat([p.grad.reshape(-1) for p in self.params])
@@ -335,8 +373,20 @@ class PPOTrainer:
         """Minibatch `self._mbi` of the current epoch, gathered ON THE DEVICE from the static full-data buffers: the index
         tensors are the only thing the host touches per SGD step, so the whole step (gather, forward, loss, backward,
         clip, Adam) is one graph replay."""
+        torch = self.torch
         idx = self._perm.index_select(0, self._mbi).reshape(-1)                          # [mb] segment ids
-        batch = {k: v.index_select(1, idx) for k, v in self._data.items()}
+        side = None
+        if self.cfg.parallel_nets:     # the value network's input (the largest gather) is fetched on the stream that consumes it
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.dev)
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            batch = {"obs_priv": self._data["obs_priv"].index_select(1, idx)}
+        batch["obs"] = self._data["obs"].index_select(1, idx)
+        batch["raw_action"] = self._data["raw_action"].index_select(1, idx)
+        # the four per-transition scalars live in one [4, T, S] buffer: one gather instead of four
+        batch.update(zip(_SCALARS, self._scal.index_select(2, idx).unbind(0)))
         batch["eps"] = self._eps.index_select(0, self._mbi)[0]
         return batch
 
@@ -380,8 +430,11 @@ class PPOTrainer:
         if not self._data:       # static buffers (their addresses are baked into the captured graph)
             nobs, npriv, S = self.abi.nobs, self.abi.npriv, self.segments
             f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=self.dev)
-            self._data = {"obs": f(T + 1, S, nobs), "obs_priv": f(T + 1, S, npriv), "raw_action": f(T, S, 12), "log_prob": f(T, S), "reward": f(T, S),
-                          "discount": f(T, S), "truncation": f(T, S)}
+            # observation rows are zero-padded to a multiple of four floats (aligned first-layer GEMMs, see _linear)
+            z = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=self.dev)
+            self._data = {"obs": z(T + 1, S, pad4(nobs)), "obs_priv": z(T + 1, S, pad4(npriv)), "raw_action": f(T, S, 12)}
+            self._scal = f(len(_SCALARS), T, S)
+            self._data.update(zip(_SCALARS, self._scal.unbind(0)))
             self._perm = torch.zeros((cfg.num_minibatches, self.mb), dtype=torch.int64, device=self.dev)
             self._eps = f(cfg.num_minibatches, T, self.mb, 12)
             self._mbi = torch.zeros(1, dtype=torch.int64, device=self.dev)
@@ -391,15 +444,16 @@ class PPOTrainer:
             sl = slice(u * n, (u + 1) * n)
             for k, src in (("obs", ro.obs_state), ("obs_priv", ro.obs_privileged), ("raw_action", ro.raw_action), ("log_prob", ro.log_prob),
                            ("reward", ro.reward), ("discount", ro.discount), ("truncation", ro.truncation)):
-                self._data[k][:, sl].copy_(src)
+                self._data[k][:, sl, ..., :src.shape[-1]].copy_(src) if k.startswith("obs") else self._data[k][:, sl].copy_(src)
             self.env_steps += T * n * self.world
         data = self._data
         reward_mean, done_rate = data["reward"].mean(), (1.0 - data["discount"]).mean()
         if cfg.normalize_observations:
-            self.norm_state.update(data["obs"][:T], self.group)
-            self.norm_priv.update(data["obs_priv"][:T], self.group)
-            data["obs"].copy_(self.norm_state.normalize(data["obs"]))
-            data["obs_priv"].copy_(self.norm_priv.normalize(data["obs_priv"]))
+            obs, priv = data["obs"][..., :self.abi.nobs], data["obs_priv"][..., :self.abi.npriv]
+            self.norm_state.update(obs[:T], self.group)
+            self.norm_priv.update(priv[:T], self.group)
+            obs.copy_(self.norm_state.normalize(obs))
+            priv.copy_(self.norm_priv.normalize(priv))
         last = {}
         for _ in range(cfg.num_updates_per_batch):
             self._perm.copy_(torch.randperm(self.segments, generator=self.gen, device=self.dev).reshape(cfg.num_minibatches, self.mb))

@@ -246,3 +246,34 @@ def test_checkpoint_resume_roundtrip(train_cfg, tmp_path):
     assert torch.equal(a.net.act(obs, deterministic=True)["action"], b.net.act(obs, deterministic=True)["action"])
     m = b.training_step()
     assert all(math.isfinite(v) for v in m.values())
+
+
+@pytest.mark.gpu
+def test_value_net_on_a_side_stream_gives_the_same_gradients():
+    """`PPOConfig.parallel_nets`: the value network's forward/backward run on a second stream; loss and gradients are the
+    ones of the single-stream evaluation."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    T, B = 20, 64
+    cfg = ppo.PPOConfig()
+    r = lambda *s: torch.randn(s, generator=g, device=dev)
+    batch = {"obs": r(T + 1, B, 171), "obs_priv": r(T + 1, B, 215), "raw_action": r(T, B, 12), "log_prob": -r(T, B).abs(), "reward": r(T, B).abs(),
+             "discount": (torch.rand((T, B), generator=g, device=dev) > 0.05).float(), "truncation": torch.zeros((T, B), device=dev), "eps": r(T, B, 12)}
+    pol = ppo.lecun_uniform_params([171, 512, 256, 128, 24], g, dev)
+    val = ppo.lecun_uniform_params([215, 512, 256, 128, 1], g, dev)
+    params = pol[0] + pol[1] + val[0] + val[1]
+    out = []
+    for side in (None, torch.cuda.Stream(dev)):
+        for p in params:
+            p.grad = None
+        loss, _ = ppo.ppo_loss(pol, val, batch, cfg, fused=True, side_stream=side)
+        loss.backward()
+        torch.cuda.synchronize()
+        out.append((float(loss.detach()), [p.grad.clone() for p in params]))
+        del loss
+    # (the head kernel accumulates its sums with float atomics: equal up to summation order)
+    assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[0][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-9
