@@ -209,6 +209,15 @@ int pgtt_ppo_head(const float* logits, const float* baseline, const float* raw_a
                   const float* vs, const float* eps, const float* adv_moments, int M, int A, float clip_eps, float entropy_cost,
                   float min_std, float* grad_logits, float* grad_baseline, float* sums, void* stream);
 
+/* One optimiser step over a flat parameter vector of n floats (all DEVICE): g' = grad * grad_scale, clipped to a global
+ * L2 norm of max_norm (coefficient min(1, max_norm / (|g'| + 1e-6)); max_norm <= 0 = no clip), then Adam with bias correction
+ * (optax.adam / torch.optim.Adam: p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)) as configured by brax ppo.train
+ * (training/train.py:135-161: learning_rate 3e-4, max_grad_norm 1.0). step: DEVICE float counter t, incremented by the call;
+ * scratch: DEVICE float[pgtt_adam_scratch_floats()]. Two launches, no host synchronisation, capturable in a CUDA graph. */
+int pgtt_adam_clip(float* param, const float* grad, float* m, float* v, float* step, float* scratch, long long n, float lr, float beta1,
+                   float beta2, float eps, float max_norm, float grad_scale, void* stream);
+int pgtt_adam_scratch_floats(void);
+
 #ifdef __cplusplus
 }
 #endif

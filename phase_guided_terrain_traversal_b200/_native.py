@@ -204,6 +204,8 @@ def declare(lib):
         lib.pgtt_rollout.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(RolloutBuffers), vp]
         lib.pgtt_gae.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp]
         lib.pgtt_ppo_head.argtypes = [vp] * 8 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+        lib.pgtt_adam_clip.argtypes = [vp] * 6 + [C.c_longlong] + [C.c_float] * 6 + [vp]
+        lib.pgtt_adam_scratch_floats.restype = C.c_int
     return lib
 
 
@@ -211,7 +213,7 @@ ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
     "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act",
-    "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_ppo_head",
+    "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_ppo_head", "pgtt_adam_clip", "pgtt_adam_scratch_floats",
 ]
 
 _LIB = None

@@ -838,6 +838,67 @@ int pgtt_ppo_head(const float* logits, const float* baseline, const float* raw_a
   return PGTT_OK;
 }
 
+// Optimiser step over one flat parameter vector: global-norm clip + Adam in two launches (see include/pgtt_b200.h).
+// Launch 1: per-block partial sums of g^2 (fixed grid, fixed order: the norm is deterministic) and the step counter;
+// launch 2: every block re-reduces the partials in the same order, then updates its grid-stride share.
+#define ADAM_BLOCKS 296
+#define ADAM_THREADS 256
+__global__ void __launch_bounds__(ADAM_THREADS) pgtt_adam_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial,
+                                                                      float* __restrict__ step) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * ADAM_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * ADAM_THREADS) { const float x = g[i]; s += x * x; }
+  __shared__ float sh[ADAM_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < ADAM_THREADS / 32; w++) t += sh[w];
+    partial[blockIdx.x] = t;
+    if (blockIdx.x == 0) *step += 1.f;
+  }
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) pgtt_adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                                       float* __restrict__ v, const float* __restrict__ partial, const float* __restrict__ step,
+                                                                       long long n, float lr, float b1, float b2, float eps, float max_norm, float grad_scale) {
+  __shared__ float coef_s;
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < ADAM_BLOCKS; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      const float norm = sqrtf(s) * grad_scale;   // norm of the scaled gradient
+      coef_s = grad_scale * (max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f);
+    }
+  }
+  __syncthreads();
+  const float coef = coef_s, t = *step;
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, rs2 = 1.f / sqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * ADAM_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * ADAM_THREADS) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * rs2 + eps);
+  }
+}
+
+int pgtt_adam_clip(float* param, const float* grad, float* m, float* v, float* step, float* scratch, long long n, float lr, float beta1, float beta2,
+                   float eps, float max_norm, float grad_scale, void* stream) {
+  if (!param || !grad || !m || !v || !step || !scratch || n <= 0) return pfail(PGTT_ERR_ARG, "pgtt_adam_clip: null argument or n <= 0");
+  pgtt_adam_sumsq_kernel<<<ADAM_BLOCKS, ADAM_THREADS, 0, (cudaStream_t)stream>>>(grad, n, scratch, step);
+  pgtt_adam_update_kernel<<<ADAM_BLOCKS, ADAM_THREADS, 0, (cudaStream_t)stream>>>(param, grad, m, v, scratch, step, n, lr, beta1, beta2, eps, max_norm, grad_scale);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
+int pgtt_adam_scratch_floats(void) { return ADAM_BLOCKS; }
+
 // generate_unroll: T x (act -> wrapped step -> record); see include/pgtt_b200.h
 static int rollout_issue(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t step0, int deterministic, const pgtt_rollout_buffers* o,
                          size_t N, int nobs, int npriv, void* stream) {

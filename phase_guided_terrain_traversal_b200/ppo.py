@@ -49,6 +49,7 @@ class PPOConfig:                      # names and defaults of training/train.py:
     seed: int = 0
     use_cuda_graph: bool = True
     fused_head: bool = True               # PPO loss head + its gradients from the hand-written kernel `pgtt_ppo_head`
+    native_optimizer: bool = True         # global-norm clip + Adam over one flat parameter vector from `pgtt_adam_clip` (two launches)
     parallel_nets: bool = True            # value network (forward and backward) on a second CUDA stream beside the policy network
     # learner GEMM precision: "highest" = fp32 like the reference (jax_default_matmul_precision=highest, train.py:94),
     # "high" = TF32 tensor cores (fp32 storage and accumulation, 10-bit mantissa products)
@@ -109,11 +110,11 @@ def _linear():
 
         class Linear(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, x, k, b):
+            def forward(ctx, x, k, b, aux):
                 pad = x.shape[1] - k.shape[0]
                 kp = torch.nn.functional.pad(k, (0, 0, 0, pad)) if pad else k
                 ctx.save_for_backward(x, kp)
-                ctx.rows = k.shape[0]
+                ctx.rows, ctx.aux = k.shape[0], aux
                 return torch.addmm(b, x, kp)
 
             @staticmethod
@@ -126,8 +127,14 @@ def _linear():
                         ones = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)     # (not cached: graph-pool memory)
                     else:
                         ones = _ONES[key] = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)
+                aux = ctx.aux
+                if aux is not None:     # parameter gradients off the critical path: only the input gradient feeds the next layer down
+                    aux.wait_stream(torch.cuda.current_stream(g.device))
+                    g.record_stream(aux); x.record_stream(aux)
+                with torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext():
+                    gk, gb = (x.t() @ g)[:ctx.rows], (ones @ g).reshape(-1)
                 gx = g @ kp.t() if ctx.needs_input_grad[0] else None
-                return gx, (x.t() @ g)[:ctx.rows], (ones @ g).reshape(-1)
+                return gx, gk, gb, None
         _LINEAR = Linear
     return _LINEAR
 
@@ -136,11 +143,13 @@ def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-def mlp(x, kernels, biases):
+def mlp(x, kernels, biases, aux=None):
+    """`aux`: CUDA stream for the parameter-gradient GEMMs of the backward pass (the caller joins it before it reads the
+    gradients); None = everything on the stream of the forward."""
     import torch
     lin = _linear()
     for i, (k, b) in enumerate(zip(kernels, biases)):
-        x = lin.apply(x.reshape(-1, x.shape[-1]), k, b).reshape(*x.shape[:-1], k.shape[1])
+        x = lin.apply(x.reshape(-1, x.shape[-1]), k, b, aux).reshape(*x.shape[:-1], k.shape[1])
         if i + 1 < len(kernels):
             x = torch.nn.functional.silu(x)
     return x
@@ -201,7 +210,7 @@ def _fused_head():
 
 
 def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_fn: Optional[Callable] = None, fused: bool = False,
-             side_stream=None):
+             side_stream=None, aux_streams=(None, None)):
     """batch: time-major [T, B, ...] tensors with NORMALISED observations `obs`, `obs_priv` ([T + 1, B, .]) plus
     raw_action, log_prob, reward, discount, truncation ([T, B]) and entropy noise `eps` [T, B, A].
     `side_stream`: the value network runs there, concurrently with the policy network (autograd replays each backward on
@@ -215,13 +224,13 @@ def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_f
         cur = torch.cuda.current_stream(batch["obs"].device)
         side_stream.wait_stream(cur)
         with torch.cuda.stream(side_stream):
-            baseline_all = mlp(batch["obs_priv"], vk, vb).squeeze(-1)   # [T + 1, B]
-        logits = mlp(batch["obs"][:T], pk, pb)
+            baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1]).squeeze(-1)   # [T + 1, B]
+        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0])
         cur.wait_stream(side_stream)
         baseline_all.record_stream(cur)
     else:
-        logits = mlp(batch["obs"][:T], pk, pb)
-        baseline_all = mlp(batch["obs_priv"], vk, vb).squeeze(-1)       # [T + 1, B]
+        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0])
+        baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1]).squeeze(-1)       # [T + 1, B]
     baseline, bootstrap = baseline_all[:T], baseline_all[T]
     rewards = batch["reward"] * cfg.reward_scaling
     truncation = batch["truncation"]
@@ -251,6 +260,48 @@ def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_f
     entropy = tanh_normal_entropy(logits, batch["eps"]).mean()
     total = policy_loss + v_loss - cfg.entropy_cost * entropy
     return total, {"total_loss": total.detach(), "policy_loss": policy_loss.detach(), "v_loss": v_loss.detach(), "entropy": entropy.detach()}
+
+
+class FlatAdam:
+    """All parameters as views of ONE flat device vector; `step(flat_grad)` = `clip_grad_norm_` + `torch.optim.Adam.step` from the
+    hand-written kernel pair `pgtt_adam_clip` (two launches instead of ~10 multi-tensor ones, 60 -> 8 us; deterministic norm).
+    `grad_scale` folds the 1 / world averaging of an all-reduced gradient into the same pass."""
+
+    def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
+        import torch
+        from . import _native as nat
+        self.lib = nat.load_library()
+        self.params = list(params)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        with torch.no_grad():
+            self.flat = torch.cat([p.detach().reshape(-1) for p in self.params]).contiguous()
+            off = 0
+            for p in self.params:
+                p.data = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.t = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
+        self.scratch = torch.zeros(int(self.lib.pgtt_adam_scratch_floats()), dtype=torch.float32, device=self.flat.device)
+
+    def flat_grad(self):
+        import torch
+        return torch.cat([p.grad.reshape(-1) for p in self.params])
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def step(self, flat_grad, max_norm: Optional[float], grad_scale: float = 1.0):
+        import ctypes as C
+        import torch
+        from . import _native as nat
+        assert flat_grad.is_contiguous() and flat_grad.numel() == self.flat.numel() and flat_grad.dtype == torch.float32
+        stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        rc = self.lib.pgtt_adam_clip(self.flat.data_ptr(), flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.t.data_ptr(),
+                                     self.scratch.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                     float(max_norm) if max_norm is not None else 0.0, float(grad_scale), stream)
+        if rc:
+            raise nat.PgttError(rc, self.lib.pgtt_policy_last_error().decode())
 
 
 class RunningStats:
@@ -320,6 +371,7 @@ class PPOTrainer:
         self.value_params = lecun_uniform_params((npriv, *cfg.value_hidden_layer_sizes, 1), gen, self.dev)
         self.params = [*self.policy_params[0], *self.policy_params[1], *self.value_params[0], *self.value_params[1]]
         self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=cfg.use_cuda_graph, fused=True)
+        self.flat_opt = FlatAdam(self.params, cfg.learning_rate, eps=1e-8) if cfg.native_optimizer else None
         self.norm_state, self.norm_priv = RunningStats(nobs, self.dev), RunningStats(npriv, self.dev)
         self.net = PolicyNet((nobs, *cfg.policy_hidden_layer_sizes, 24), device=self.abi.device)
         self.collector = RolloutCollector(wenv, self.net, unroll_length=cfg.unroll_length, seed=cfg.seed * 7919 + self.rank)
@@ -329,6 +381,7 @@ class PPOTrainer:
         self.env_steps = 0
         self._graph = None
         self._side = None
+        self._aux = None
         self._data: Dict = {}
         self.metrics: Dict = {}
         self._sync_policy()
@@ -350,12 +403,25 @@ class PPOTrainer:
 
     def _sgd_body(self, batch):
         torch = self.torch
-        if self.cfg.parallel_nets and self._side is None:
+        par = self.cfg.parallel_nets
+        if par and self._side is None:
             self._side = torch.cuda.Stream(self.dev)
+        if par and self._aux is None:
+            self._aux = (torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev))
         loss, m = ppo_loss(self.policy_params, self.value_params, batch, self.cfg, self._moments, fused=self.cfg.fused_head,
-                           side_stream=self._side if self.cfg.parallel_nets else None)
+                           side_stream=self._side if par else None, aux_streams=self._aux if par else (None, None))
         self.opt.zero_grad(set_to_none=True)    # backward writes fresh gradients: no fill + accumulate pair per parameter
         loss.backward()
+        if par:   # the parameter-gradient branches rejoin before anything reads the gradients
+            cur = torch.cuda.current_stream(self.dev)
+            for a in self._aux:
+                cur.wait_stream(a)
+        if self.flat_opt is not None:
+            flat = self.flat_opt.flat_grad()
+            if self.world > 1:
+                torch.distributed.all_reduce(flat, group=self.group)
+            self.flat_opt.step(flat, self.cfg.max_grad_norm, 1.0 / self.world)
+            return m
         if self.world > 1:
             flat = torch.cat([p.grad.reshape(-1) for p in self.params])
             torch.distributed.all_reduce(flat, group=self.group)

@@ -250,7 +250,7 @@ def test_checkpoint_resume_roundtrip(train_cfg, tmp_path):
 
 @pytest.mark.gpu
 def test_value_net_on_a_side_stream_gives_the_same_gradients():
-    """`PPOConfig.parallel_nets`: the value network's forward/backward run on a second stream; loss and gradients are the
+    """`PPOConfig.parallel_nets`: the value network's forward/backward run on a second stream and the parameter-gradient GEMMs on two more; loss and gradients are the
     ones of the single-stream evaluation."""
     import torch
     from phase_guided_terrain_traversal_b200 import ppo
@@ -265,10 +265,10 @@ def test_value_net_on_a_side_stream_gives_the_same_gradients():
     val = ppo.lecun_uniform_params([215, 512, 256, 128, 1], g, dev)
     params = pol[0] + pol[1] + val[0] + val[1]
     out = []
-    for side in (None, torch.cuda.Stream(dev)):
+    for side, aux in ((None, (None, None)), (torch.cuda.Stream(dev), (torch.cuda.Stream(dev), torch.cuda.Stream(dev)))):
         for p in params:
             p.grad = None
-        loss, _ = ppo.ppo_loss(pol, val, batch, cfg, fused=True, side_stream=side)
+        loss, _ = ppo.ppo_loss(pol, val, batch, cfg, fused=True, side_stream=side, aux_streams=aux)
         loss.backward()
         torch.cuda.synchronize()
         out.append((float(loss.detach()), [p.grad.clone() for p in params]))
@@ -277,3 +277,32 @@ def test_value_net_on_a_side_stream_gives_the_same_gradients():
     assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[0][0])
     for a, b in zip(out[0][1], out[1][1]):
         assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_norm", [1.0, None])
+def test_native_clip_adam_matches_torch(max_norm):
+    """`pgtt_adam_clip` (flat vector, two launches) against `clip_grad_norm_` + `torch.optim.Adam` over six steps with gradients
+    large enough to be clipped: parameters agree to float rounding."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    shapes = [(171, 512), (512,), (512, 256), (256,), (128, 24), (24,), (215, 512), (1,)]
+    ref = [torch.randn(s, generator=g, device=dev).requires_grad_() for s in shapes]
+    mine = [p.detach().clone().requires_grad_() for p in ref]
+    opt = torch.optim.Adam(ref, lr=3e-4, eps=1e-8)
+    flat = ppo.FlatAdam(mine, 3e-4, eps=1e-8)
+    for step in range(6):
+        grads = [torch.randn(s, generator=g, device=dev) * (0.05 if step % 2 else 0.001) for s in shapes]
+        for p, q, gr in zip(ref, mine, grads):
+            p.grad = gr.clone(); q.grad = gr.clone() * 4.0       # the native step is given 4 x the gradient and grad_scale = 1/4
+        if max_norm is not None:
+            torch.nn.utils.clip_grad_norm_(ref, max_norm)
+        opt.step()
+        flat.step(flat.flat_grad(), max_norm, 0.25)
+        flat.zero_grad()
+    torch.cuda.synchronize()
+    assert float(flat.t) == 6.0
+    for p, q in zip(ref, mine):
+        assert q.data_ptr() >= flat.flat.data_ptr() and float((p - q).detach().abs().max()) <= 2e-6 * max(float(p.detach().abs().max()), 1.0)

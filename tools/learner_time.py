@@ -9,7 +9,7 @@ import functools
 for prec in (sys.argv[1:] or ["highest", "high"]):
     n=4096
     import os
-    cfg=ppo.PPOConfig(num_envs=n, matmul_precision=prec, parallel_nets=os.environ.get("PGTT_PAR","1")=="1")
+    cfg=ppo.PPOConfig(num_envs=n, matmul_precision=prec, parallel_nets=os.environ.get("PGTT_PAR","1")=="1", native_optimizer=os.environ.get("PGTT_NOPT","1")=="1")
     env=Joystick(task="stairs", config=training_overrides(default_config()))
     keys=prng.env_keys(1,n)
     wenv=wrap_for_brax_training(env, episode_length=1000, randomization_fn=functools.partial(domain_randomize, rng=keys, terrain_matrix=terrain.load_terrain("level1"), dynamics=True))
