@@ -418,3 +418,35 @@ def test_baseline_sizes_against_the_oracle(cfgname, n, level, dyn, train_cfg):
             x, y = orc.get(a)[same], env.get(b).astype(np.float64)[same]
             err = np.abs(x - y).max(1)
             assert err.max() <= tol * max(np.abs(x).max(), 1.0), (cfgname, s, a, err.max(), np.quantile(err, 0.999))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cuda", "cuda-quad"])
+def test_long_horizon_bookkeeping_matches_the_oracle(kind, train_cfg):
+    """1010 wrapped control steps of 32 standing robots (flat terrain, small actions: nobody falls, so the chaotic part of
+    the dynamics cannot desynchronise the two sides): the per-env random command resamplings (joystick_pgtt.py:210-221) and
+    the episode truncation at step 1000 (EpisodeWrapper) land on the same steps with the same draws - rng, counters,
+    truncation flags bit-exact, commands to 1e-6 - and observations still agree to 1e-3 after 20 s of simulated time."""
+    n = 32
+    m, orc, env, keys = setup_pair(kind, "flat_terrain", train_cfg, dyn=True, n=n)
+    orc.reset(keys + 9); env.reset(keys + 9)
+    rng = np.random.default_rng(77)
+    cmd0 = env.get("command").copy()
+    resampled_at, truncated_at = [], []
+    for s in range(1010):
+        act = (0.1 * rng.uniform(-1, 1, (n, 12))).astype(np.float32)
+        orc.step(act.astype(np.float64)); env.step(act)
+        if s % 50 == 49 or s in (499, 500, 999, 1000):
+            for a in ("rng", "step", "steps_until_next_cmd", "steps", "truncation", "done"):
+                assert np.array_equal(orc.get(a), env.get(a).astype(np.float64)), (s, a)
+            assert np.abs(orc.get("command") - env.get("command")).max() < 1e-6, s
+        c = env.get("command")
+        if not np.array_equal(c, cmd0):
+            resampled_at.append(s); cmd0 = c.copy()
+        if env.get("truncation").any():
+            truncated_at.append(s)
+    assert env.get("done").sum() == 0 or truncated_at          # nobody fell
+    assert truncated_at == [999], truncated_at                  # the 1000th step of the episode
+    assert len(resampled_at) > 20, resampled_at                 # per-env random resampling times were exercised many times
+    err = np.abs(orc.get("obs_state") - env.get("obs_state")).max()
+    assert err < 1e-3 * max(np.abs(orc.get("obs_state")).max(), 1.0), err
