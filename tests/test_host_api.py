@@ -10,6 +10,7 @@ import pytest
 
 import phase_guided_terrain_traversal_b200 as pkg
 from phase_guided_terrain_traversal_b200 import _native as nat
+from phase_guided_terrain_traversal_b200 import model as gm
 from phase_guided_terrain_traversal_b200 import prng, registry, terrain
 from phase_guided_terrain_traversal_b200.go2 import configs, go2_constants as consts
 
@@ -124,3 +125,31 @@ def test_key_helpers():
         prng.as_keys(np.zeros((3, 3)))
     with pytest.raises(ValueError):
         prng.as_keys(k, 6)
+
+
+def test_abi_rejects_bad_arguments_without_touching_a_device():
+    """Error behaviour of the C ABI: null pointers / empty shapes return PGTT_ERR_ARG (-1) with a message from
+    pgtt_last_error / pgtt_policy_last_error before any CUDA call is made, so this runs on a host without a GPU."""
+    nat.build_library()
+    try:
+        lib = nat.declare(ctypes.CDLL(str(nat.LIB_PATH)))
+    except OSError as e:
+        pytest.skip(f"CUDA runtime not loadable on this host: {e}")
+    lib.pgtt_last_error.restype = ctypes.c_char_p
+    null = ctypes.c_void_p(0)
+    out = ctypes.c_void_p(0)
+    assert lib.pgtt_create(None, None, 0, 16, ctypes.byref(out)) == -1 and b"pgtt_create" in lib.pgtt_last_error()
+    m = gm.compile_model("flat_terrain")
+    md, td = nat.model_desc(m), nat.task_desc(configs.default_config(), m)
+    assert lib.pgtt_create(ctypes.byref(md), ctypes.byref(td), 0, 0, ctypes.byref(out)) == -1          # num_envs <= 0
+    assert out.value is None
+    for call in (lambda: lib.pgtt_sync(null, null), lambda: lib.pgtt_set_terrain_table(null, null, 0),
+                 lambda: lib.pgtt_randomize(null, null, 0, null), lambda: lib.pgtt_get_buffers(null, None),
+                 lambda: lib.pgtt_obs_dims(null, None, None), lambda: lib.pgtt_record(null, null, null, null, null, null, null)):
+        assert call() == -1 and lib.pgtt_last_error()
+    assert lib.pgtt_step_kernel_generation(null) == -1
+    assert lib.pgtt_destroy(null) == 0                                                                 # destroying nothing is fine
+    assert lib.pgtt_gae(null, null, null, null, 0, 0, 0.95, 0.97, 1.0, null, null, null) == -1 and b"pgtt_gae" in lib.pgtt_policy_last_error()
+    assert lib.pgtt_ppo_head(*([null] * 8), 0, 12, 0.3, 0.01, 0.001, null, null, null, null) == -1
+    assert lib.pgtt_adam_clip(*([null] * 6), 0, 3e-4, 0.9, 0.999, 1e-8, 1.0, 1.0, null) == -1 and b"pgtt_adam_clip" in lib.pgtt_policy_last_error()
+    assert lib.pgtt_adam_scratch_floats() > 0
