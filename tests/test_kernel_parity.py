@@ -59,15 +59,15 @@ def setup_pair(kind, task, cfg, dyn=True, part=True, seed_hi=7, level="level07",
 
 
 @pytest.mark.parametrize("kind", BACKENDS)
-@pytest.mark.parametrize("task", ["flat_terrain", "stairs"])
-def test_forward_stage_by_stage(kind, task, train_cfg):
-    m, orc, env, _ = setup_pair(kind, task, train_cfg)
+@pytest.mark.parametrize("task,seed,level", [("flat_terrain", 3, None), ("stairs", 3, "level07"), ("stairs", 17, "level13")])
+def test_forward_stage_by_stage(kind, task, seed, level, train_cfg):
+    m, orc, env, _ = setup_pair(kind, task, train_cfg, level=level or "level07")
     # per-env model written by the randomiser is bit-identical
     assert np.array_equal(orc.get("terrain_index")[:, 0], env.get("terrain_index")[:, 0]) or task == "flat_terrain"
     for a, b, sl in [("m_body_mass", "body_mass", slice(1, None)), ("m_dof_armature", "dof_armature", slice(6, None)),
                      ("m_dof_damping", "dof_damping", slice(6, None)), ("m_qpos0", "qpos0", slice(7, None)), ("m_act_gain", "actuator_gain", slice(None))]:
         assert np.array_equal(orc.get(a)[:, sl].astype(np.float32), env.get(b)), a
-    qpos, qvel, ctrl, warm = random_states(m, N, 3)
+    qpos, qvel, ctrl, warm = random_states(m, N, seed)
     for k, v in (("qpos", qpos), ("qvel", qvel), ("ctrl", ctrl), ("qacc_warmstart", warm)):
         orc.set(k, v); env.set(k, v.astype(np.float32))
     orc.forward()
