@@ -1286,27 +1286,45 @@ DEV void q_heightscan(QShared& Sh, const QModel& M, float cx, float cyy, float c
     }
     syncwarp();
   }
-  for (int r = g; r < NRAY; r += 4) {
+  // rays of this lane (r = g, g + 4, ...) stay in registers; the box loop is the OUTER loop so that each listed box is
+  // fetched once per lane instead of once per ray. Per (ray, box) pair the arithmetic is unchanged and min() does not
+  // depend on the order of the boxes: bit-identical to the ray-outer form.
+  constexpr int RPL = (NRAY + 3) / 4;
+  float ox[RPL], oy[RPL], best[RPL];
+#pragma unroll
+  for (int q = 0; q < RPL; q++) {
+    const int r = (g + 4 * q < NRAY) ? g + 4 * q : NRAY - 1;
     const int i = r / NRAY_W, j = r % NRAY_W;
     const float p = (6.0f - (float)i) * 0.1f, k = (4.0f - (float)j) * 0.1f;
-    float ox = cx + (p * cy - k * sy), oy = cyy + (p * sy + k * cy);
-    if (i == 6 && j == 4) { ox = cx; oy = cyy; }
-    float best = Q_INF;
-    if (oz >= 0.f) best = oz;  // floor plane z = 0
-    for (int t = 0; t < nl; t++) {
-      const int kb = Sh.boxlist[slot][t];
-      const float4 b0 = ldg4(bp + 2 * kb), b1 = ldg4(bp + 2 * kb + 1);
-      const float rx = ox - b0.x, ry = oy - b0.y, lz = oz - b0.z;
+    ox[q] = cx + (p * cy - k * sy); oy[q] = cyy + (p * sy + k * cy);
+    if (i == 6 && j == 4) { ox[q] = cx; oy[q] = cyy; }
+    best[q] = Q_INF;
+    if (oz >= 0.f) best[q] = oz;  // floor plane z = 0
+  }
+#pragma unroll 1
+  for (int t = 0; t < nl; t++) {
+    const int kb = Sh.boxlist[slot][t];
+    const float4 b0 = ldg4(bp + 2 * kb), b1 = ldg4(bp + 2 * kb + 1);
+    const float lz = oz - b0.z;
+    const float ttop = lz - b1.y, tbot = lz + b1.y;
+#pragma unroll
+    for (int q = 0; q < RPL; q++) {
+      const float rx = ox[q] - b0.x, ry = oy[q] - b0.y;
       const float lx = b1.z * rx + b1.w * ry, ly = -b1.w * rx + b1.z * ry;
       if (fabsf(lx) <= b0.w && fabsf(ly) <= b1.x) {
-        const float ttop = lz - b1.y, tbot = lz + b1.y;
-        if (ttop >= 0.f) best = fminf(best, ttop);
-        else if (tbot >= 0.f) best = fminf(best, tbot);
+        if (ttop >= 0.f) best[q] = fminf(best[q], ttop);
+        else if (tbot >= 0.f) best[q] = fminf(best[q], tbot);
       }
     }
-    const float z = oz - best;
-    if (out) { out[3 * r] = ox; out[3 * r + 1] = oy; out[3 * r + 2] = z; }
-    Sh.scan[slot][r] = z;
+  }
+#pragma unroll
+  for (int q = 0; q < RPL; q++) {
+    const int r = g + 4 * q;
+    if (r < NRAY) {
+      const float z = oz - best[q];
+      if (out) { out[3 * r] = ox[q]; out[3 * r + 1] = oy[q]; out[3 * r + 2] = z; }
+      Sh.scan[slot][r] = z;
+    }
   }
   syncwarp();
 }
