@@ -489,14 +489,29 @@ DEV void q_build_near(QNear& Nr, QShared& S, const QModel& M, const float* foot,
   const float rp = (GC.foot_r + Q_MARGIN) * 1.001f, rc = (Q_RCEN + Q_MARGIN) * 1.001f;
   const float rp2 = rp * rp, rc2 = rc * rc;
   int npen = 0, ncen = 0;
-#pragma unroll 4
-  for (int k = 0; k < nb; k++) {
-    const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
-    const float dx = b0.x - foot[0], dy = b0.y - foot[1], dz = b0.z - foot[2];
-    const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
-    const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
-    if (e0 * e0 + e1 * e1 + e2 * e2 < rp2) { if (npen < QPEN) S.pen_list[npen][lane] = k; npen++; }
-    if (dx * dx + dy * dy + dz * dz < rc2) { if (ncen < QCEN) S.cen_list[ncen][lane] = k; ncen++; }
+  // the box table of an env (3.2 KB, one of 100 per level) is L2-resident, not L1-resident: fetch ten boxes (twenty
+  // 16-byte loads in flight) per round trip instead of leaving the trip count to the unroller
+  constexpr int CH = 10;
+#pragma unroll 1
+  for (int k0 = 0; k0 < nb; k0 += CH) {
+    float4 c0[CH], c1[CH];
+#pragma unroll
+    for (int u = 0; u < CH; u++) {
+      const int k = (k0 + u < nb) ? k0 + u : nb - 1;
+      c0[u] = ldg4(bp + 2 * k); c1[u] = ldg4(bp + 2 * k + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < CH; u++) {
+      const int k = k0 + u;
+      if (k < nb) {
+        const float4 b0 = c0[u], b1 = c1[u];
+        const float dx = b0.x - foot[0], dy = b0.y - foot[1], dz = b0.z - foot[2];
+        const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
+        const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
+        if (e0 * e0 + e1 * e1 + e2 * e2 < rp2) { if (npen < QPEN) S.pen_list[npen][lane] = k; npen++; }
+        if (dx * dx + dy * dy + dz * dz < rc2) { if (ncen < QCEN) S.cen_list[ncen][lane] = k; ncen++; }
+      }
+    }
   }
   Nr.f0[0] = foot[0]; Nr.f0[1] = foot[1]; Nr.f0[2] = foot[2];
   Nr.npen = npen; Nr.ncen = ncen; Nr.over = (npen > QPEN) || (ncen > QCEN);
@@ -523,6 +538,7 @@ DEV void q_collide_boxes(QGeo& GX, QNear& Nr, bool build, QShared& S, const QKin
   int ncand = 0;
   {
     const int cnt = full ? nb : Nr.npen;
+#pragma unroll 2
     for (int i = 0; i < cnt; i++) {
       const int k = full ? i : S.pen_list[i][lane];
       const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
@@ -557,6 +573,7 @@ DEV void q_collide_boxes(QGeo& GX, QNear& Nr, bool build, QShared& S, const QKin
 #pragma unroll
       for (int s = 0; s < 4; s++) { t[s] = shfl(myt, qbase | s); id[s] = shfl(myid, qbase | s); cnt[s] = 0; }
       const int n2 = full2 ? nb : Nr.ncen;
+#pragma unroll 4
       for (int i = 0; i < n2; i++) {
         const int k = full2 ? i : S.cen_list[i][lane];
         const float4 b0 = ldg4(bp + 2 * k);
@@ -1270,19 +1287,30 @@ DEV void q_heightscan(QShared& Sh, const QModel& M, float cx, float cyy, float c
   int nl = 0;
   if (nb > 0) {
     const unsigned lt = (1u << g) - 1u;
+    constexpr int HCH = 5;   // five boxes per lane per round trip to L2 (see q_build_near)
+    static_assert(((NBOX + 3) / 4) % HCH == 0, "chunking of the heightscan list build");
 #pragma unroll 1
-    for (int it = 0; it < (NBOX + 3) / 4; it++) {
-      const int k = it * 4 + g;
-      bool near = false;
-      if (k < nb) {
-        const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
-        const float dx = b0.x - cx, dy = b0.y - cyy;
-        const float rad = sqrtf(b0.w * b0.w + b1.x * b1.x) + 0.75f;  // grid half-diagonal 0.7211 + slack
-        near = dx * dx + dy * dy <= rad * rad;
+    for (int it0 = 0; it0 < (NBOX + 3) / 4; it0 += HCH) {
+      float4 c0[HCH], c1[HCH];
+#pragma unroll
+      for (int u = 0; u < HCH; u++) {
+        const int k = (it0 + u) * 4 + g, kc = k < nb ? k : nb - 1;
+        c0[u] = ldg4(bp + 2 * kc); c1[u] = ldg4(bp + 2 * kc + 1);
       }
-      const unsigned nib = (wballot(near) >> qbase) & 0xFu;
-      if (near) Sh.boxlist[slot][nl + popc(nib & lt)] = k;
-      nl += popc(nib);
+#pragma unroll
+      for (int u = 0; u < HCH; u++) {
+        const int k = (it0 + u) * 4 + g;
+        bool near = false;
+        if (k < nb) {
+          const float4 b0 = c0[u], b1 = c1[u];
+          const float dx = b0.x - cx, dy = b0.y - cyy;
+          const float rad = sqrtf(b0.w * b0.w + b1.x * b1.x) + 0.75f;  // grid half-diagonal 0.7211 + slack
+          near = dx * dx + dy * dy <= rad * rad;
+        }
+        const unsigned nib = (wballot(near) >> qbase) & 0xFu;
+        if (near) Sh.boxlist[slot][nl + popc(nib & lt)] = k;
+        nl += popc(nib);
+      }
     }
     syncwarp();
   }
