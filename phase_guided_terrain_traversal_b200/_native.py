@@ -221,7 +221,7 @@ _LIB = None
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """nvcc -> csrc/libpgtt_b200.so (in-tree, so it travels to the GPU box with the snapshot)."""
-    srcs = [CSRC / n for n in ("pgtt_api.cu", "pgtt_policy.cu", "pgtt_env.cuh", "pgtt_quad.cuh", "pgtt_physics.cuh", "pgtt_types.h", "simt.h", "pgtt_debug.h")] + [INCLUDE / "pgtt_b200.h"]
+    srcs = sorted(CSRC.glob("*.cu*")) + sorted(CSRC.glob("*.h")) + [INCLUDE / "pgtt_b200.h"]      # every kernel source and header
     newest = max(s.stat().st_mtime for s in srcs)
     if not force and LIB_PATH.exists() and LIB_PATH.stat().st_mtime >= newest:
         return LIB_PATH
