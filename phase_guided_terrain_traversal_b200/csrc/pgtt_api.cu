@@ -366,6 +366,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   c.sync_mask = (1 << ST_COLLIDE) | (1 << ST_PRESOLVE) | (1 << ST_POSTSOLVE);
   if (const char* sm = getenv("PGTT_SYNC_MASK")) c.sync_mask = (int)strtol(sm, nullptr, 0);
   if (const char* fs = getenv("PGTT_QUAD_FULLSCAN")) c.quad_fullscan = atoi(fs) != 0;
+  if (const char* lv = getenv("PGTT_QUAD_LS_VOTE")) c.quad_ls_vote = atoi(lv) != 0;
   c.iterations = m->iterations; c.ls_iterations = m->ls_iterations; c.max_geom_pairs = m->max_geom_pairs;
   c.max_contact_points = m->max_contact_points; c.n_boxes = m->n_boxes; c.n_substeps = t->n_substeps;
   for (int b = 0; b < NB; b++) {

@@ -947,13 +947,17 @@ DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, co
   QLSPoint hi = lesser ? p0 : l0, lo = lesser ? l0 : p0;
   bool swap = true;
   int it = 0;
+  // An env takes at most ls_iterations rounds and the 64 envs of a lockstep CTA practically always contain one that takes
+  // them all (8 envs: 4.88 of 5 on average), so the loop runs the full count without a CTA vote per round (one barrier
+  // less per round; rounds of finished envs are predicated off, as they were under the vote). The Newton-level vote
+  // re-aligns the warps once per Newton iteration.
 #pragma unroll 1
-  for (;;) {
+  for (int round = 0;; round++) {
     bool done = !live || it >= GC.ls_iterations;
     done |= (!swap) && (it > 0);
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
-    if (cta_all(done)) break;
+    if (GC.quad_ls_vote ? cta_all(done) : (round >= GC.ls_iterations)) break;
     QLSPoint pts[3];
     const float al3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
     q_ls_eval<3>(pts, al3, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);

@@ -25,6 +25,7 @@ struct ModelConst {
   float dt, gravity_z, impratio, tolerance, ls_tolerance, meaninertia, solver_scale;
   int iterations, ls_iterations, max_geom_pairs, max_contact_points, n_boxes, n_substeps;
   int sync_mask;   // which stages end in a CTA barrier (tuning knob, pgtt_api.cu)
+  int quad_ls_vote;    // quad kernel: line-search loop exits on a CTA vote per iteration (PGTT_QUAD_LS_VOTE=1) instead of running ls_iterations rounds
   int quad_fullscan;   // quad kernel: always scan all boxes instead of the per-step near lists (test knob, PGTT_QUAD_FULLSCAN=1)
   float body_pos[NB][3], body_ipos[NB][3], body_I[NB][6];  // body-frame inertia tensor xx yy zz xy xz yz
   float jnt_lo[12], jnt_hi[12], dof_invw[12], calf_invw[4];
