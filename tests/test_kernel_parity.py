@@ -450,3 +450,29 @@ def test_long_horizon_bookkeeping_matches_the_oracle(kind, train_cfg):
     assert len(resampled_at) > 20, resampled_at                 # per-env random resampling times were exercised many times
     err = np.abs(orc.get("obs_state") - env.get("obs_state")).max()
     assert err < 1e-3 * max(np.abs(orc.get("obs_state")).max(), 1.0), err
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_platform_equals_floor_shifted(kind, train_cfg):
+    """The kernels' box-contact path against their own plane-contact path (tests/test_oracle_physics.py has the float64
+    version): 16 robots standing on a 0.2 m platform and 16 on the floor receive the same actions for 10 control steps;
+    joint angles, base attitude and base height minus 0.2 m agree to 2e-4 (fp32, a shifted z rounds differently)."""
+    from test_oracle_physics import _platform_table
+    h = 0.2
+    mf, ms = gm.compile_model("flat_terrain"), gm.compile_model("stairs")
+    keys = keys_for(N, 5)
+    ef, eb = make_env(kind, mf, train_cfg, N), make_env(kind, ms, train_cfg, N)
+    ef.randomize(keys, False); eb.set_terrain(_platform_table(h)); eb.randomize(keys, False)
+    ef.reset(keys); eb.reset(keys)
+    q = np.tile(mf.home_qpos, (N, 1)).astype(np.float32)
+    ef.set("qpos", q); ef.set("qvel", np.zeros((N, 18), np.float32))
+    qb = q.copy(); qb[:, 2] += h
+    eb.set("qpos", qb); eb.set("qvel", np.zeros((N, 18), np.float32))
+    rng = np.random.default_rng(1)
+    for s in range(10):
+        act = (0.3 * rng.uniform(-1, 1, (N, 12))).astype(np.float32)
+        ef.step(act, wrapped=False); eb.step(act, wrapped=False)
+    a, b = ef.get("qpos"), eb.get("qpos").copy()
+    b[:, 2] -= h
+    assert np.abs(a - b).max() < 2e-4, np.abs(a - b).max()
+    assert (eb.get("contact_geom")[:, 8:] >= 0).any() and np.array_equal(ef.get("contact"), eb.get("contact"))

@@ -141,3 +141,40 @@ def test_standing_on_floor(flat_model, train_cfg):
     s = orc.get("sensordata")[0]
     assert np.allclose(s[3:6], [0, 0, 9.81], atol=0.3)     # accelerometer at rest
     assert s[24] > 0.99                                     # up-vector
+
+
+def _platform_table(h):
+    """One terrain whose box 0 is a 6 m x 6 m platform of height h under the robot; the other 99 boxes are pebbles 50 m away."""
+    table = np.zeros((1, 100, 10), np.float32)
+    table[0, :, 3] = 1.0
+    table[0, :, 0] = 50 + np.arange(100); table[0, :, 1] = 50; table[0, :, 2] = 0.01; table[0, :, 7:] = 0.01
+    table[0, 0] = [0, 0, h / 2, 1, 0, 0, 0, 3, 3, h / 2]
+    return table
+
+
+def test_box_contacts_reproduce_plane_contacts_on_a_platform(train_cfg):
+    """Translation invariance as a cross-check of two independent code paths: a robot on a large box of height h (sphere/box
+    collision, box contact slots, culling, box friction) must move exactly like a robot on the floor (sphere/plane path),
+    shifted by h. 200 physics steps with random joint targets, float64 oracle: agreement to 1e-7."""
+    h = 0.2
+    mf, ms = gm.compile_model("flat_terrain"), gm.compile_model("stairs")
+    keys = np.array([[0, 1]], np.uint32)
+    of, ob = Oracle(mf, train_cfg, 1, "f64"), Oracle(ms, train_cfg, 1, "f64")
+    of.randomize(keys, None, False); ob.randomize(keys, _platform_table(h), False)
+    q = mf.home_qpos.copy()
+    for o, dz in ((of, 0.0), (ob, h)):
+        qq = q.copy(); qq[2] += dz
+        o.set("qpos", qq[None]); o.set("qvel", np.zeros((1, 18))); o.set("ctrl", q[7:][None])
+    rng = np.random.default_rng(0)
+    for s in range(200):
+        c = q[7:] + 0.2 * rng.uniform(-1, 1, 12)
+        of.set("ctrl", c[None]); ob.set("ctrl", c[None])
+        of.physics_step(); ob.physics_step()
+    a, b = of.get("qpos")[0], ob.get("qpos")[0].copy()
+    b[2] -= h
+    assert np.abs(a - b).max() < 1e-7 and np.abs(of.get("qvel")[0] - ob.get("qvel")[0]).max() < 1e-6
+    _, kf = of.contacts(0)
+    fb, kb = ob.contacts(0)
+    assert (kf[:4, 4] == -1).all() and (kf[4:, 0] == -1).all()              # floor run: four plane slots, no box slot
+    assert (kb[4:, 4] == 0).all() and (fb[4:, 0] < 0).all()                 # platform run: all four feet penetrate box 0 ...
+    assert (fb[:4, 0] > 0.19).all()                                         # ... and are 0.2 m above the plane
