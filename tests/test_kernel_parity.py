@@ -476,3 +476,31 @@ def test_platform_equals_floor_shifted(kind, train_cfg):
     b[:, 2] -= h
     assert np.abs(a - b).max() < 2e-4, np.abs(a - b).max()
     assert (eb.get("contact_geom")[:, 8:] >= 0).any() and np.array_equal(ef.get("contact"), eb.get("contact"))
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_kernels_respect_quarter_turn_and_mirror_symmetry(kind, train_cfg):
+    """The symmetries of tests/test_oracle_physics.py::test_quarter_turn_and_mirror_symmetry on the kernels themselves (the
+    quad-per-env kernel gives each lane its own leg's constant record: a wrong sign in one record breaks the mirror):
+    16 random moving states, their quarter-turned and mirrored images, 5 control steps with (mirrored) actions."""
+    from test_oracle_physics import _moving_state, mirror_legs, mirror_state, quarter_turn
+    m = gm.compile_model("flat_terrain")
+    states = [_moving_state(m, 100 + i)[:2] for i in range(N)]
+    rng = np.random.default_rng(4)
+    acts = [(0.5 * rng.uniform(-1, 1, (N, 12))).astype(np.float32) for _ in range(5)]
+    out = []
+    for tf, tact in ((lambda q, v: (q, v), lambda a: a), (quarter_turn, lambda a: a), (mirror_state, mirror_legs)):
+        env = make_env(kind, m, train_cfg, N)
+        keys = keys_for(N, 2)
+        env.randomize(keys, False); env.reset(keys)
+        qv = [tf(q, v) for q, v in states]
+        env.set("qpos", np.stack([x[0] for x in qv]).astype(np.float32)); env.set("qvel", np.stack([x[1] for x in qv]).astype(np.float32))
+        for a in acts:
+            env.step(np.stack([tact(r) for r in a]).astype(np.float32), wrapped=False)
+        out.append((env.get("qpos").astype(np.float64), env.get("qvel").astype(np.float64)))
+    (qa, va), (qt, vt), (qm, vm) = out
+    for i in range(N):
+        qe, _ = quarter_turn(qa[i], va[i])
+        assert np.abs(qe - qt[i]).max() < 1e-4, ("quarter turn", i, np.abs(qe - qt[i]).max())
+        qe, _ = mirror_state(qa[i], va[i])
+        assert np.abs(qe - qm[i]).max() < 5e-4, ("mirror", i, np.abs(qe - qm[i]).max())
