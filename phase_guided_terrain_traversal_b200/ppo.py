@@ -127,6 +127,8 @@ def _linear():
                         ones = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)     # (not cached: graph-pool memory)
                     else:
                         ones = _ONES[key] = torch.ones((1, g.shape[0]), device=g.device, dtype=g.dtype)
+                        if g.is_cuda:      # shared by every stream from now on: make sure it is written before any of them reads it
+                            torch.cuda.current_stream(g.device).synchronize()
                 aux = ctx.aux
                 if aux is not None:     # parameter gradients off the critical path: only the input gradient feeds the next layer down
                     aux.wait_stream(torch.cuda.current_stream(g.device))
