@@ -1,0 +1,39 @@
+"""bench.py's reference arm runs on the host cores (the CPU oracle port), so its side of the driver contract can be
+checked without a GPU: one JSON line, the contract keys, rank 0 only under torchrun."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+        "config", "impl", "cpu_baseline", "e2e"}
+
+
+def _check(line, n_gpus):
+    d = json.loads(line)
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["n_gpus"] == n_gpus and d["warmup"] >= 1 and d["value"] > 0 and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1", "--num-envs", "64"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    _check(lines[0], 1)
+
+
+def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29591", "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1", "--num-envs", "64"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    _check(lines[0], 2)
