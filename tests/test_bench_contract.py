@@ -37,3 +37,24 @@ def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     _check(lines[0], 2)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_b200_arm_line_carries_roofline_baseline_e2e_and_clocks():
+    """The product arm on one GPU, short run: the keys the driver and the judge read, with sane values."""
+    out = subprocess.run([sys.executable, "bench.py", "--steps", "20", "--warmup", "3", "--cpu-seconds", "2"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert (KEYS - {"impl"}) | {"roofline", "gpu_launches", "clocks", "rollout"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["scaling"] == "weak" and d["gpu_launches"] == 20
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["kernel"].startswith("pgtt_")
+    assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 12 * 4 and d["e2e"]["d2h_bytes_per_step"] == 4096 * 2 * 4 and 0 < d["e2e"]["value"] <= d["value"] * 1.05
+    assert d["cpu_baseline"]["kind"] == "port" and 0 < d["cpu_baseline"]["value"] < d["value"] / 10      # the north-star's >= 10x
+    assert d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["health"]["state_finite"] is True
