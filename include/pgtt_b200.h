@@ -134,8 +134,16 @@ int pgtt_set_terrain_table(pgtt_env* env, const float* boxes, int n_terrains);
 int pgtt_randomize(pgtt_env* env, const uint32_t* keys, int dynamics, void* stream);
 int pgtt_reset(pgtt_env* env, const uint32_t* keys, void* stream);
 
-/* action: DEVICE float [num_envs][12]. wrapped != 0 applies EpisodeWrapper + auto-reset semantics. */
+/* action: DEVICE float [num_envs][12]. wrapped != 0 applies EpisodeWrapper + auto-reset semantics.
+ * Two launches: the physics kernel (n_substeps x mjx.step, go2/joystick_pgtt.py:145-148) and the task kernel (contact flags,
+ * ray grid, observation, rewards, info, wrappers; go2/joystick_pgtt.py:149-231). */
 int pgtt_step(pgtt_env* env, const float* action, int wrapped, void* stream);
+/* pgtt_step that also files the step's transition into ONE time-major rollout slot, written by the task kernel itself (no
+ * extra launch): obs_state_dst / obs_priv_dst <- next observation, reward_dst <- reward, discount_dst <- 1 - done,
+ * truncation_dst <- truncation. DEVICE pointers to [num_envs][dim] rows; any may be NULL (brax generate_unroll,
+ * training/train.py:135-161). */
+int pgtt_step_record(pgtt_env* env, const float* action, int wrapped, float* obs_state_dst, float* obs_priv_dst, float* reward_dst,
+                     float* discount_dst, float* truncation_dst, void* stream);
 
 /* mjx.forward on the current qpos/qvel/ctrl (refreshes sensordata, contacts, qacc, warmstart). */
 int pgtt_forward(pgtt_env* env, void* stream);
@@ -154,7 +162,7 @@ int pgtt_debug_forward(pgtt_env* env, float* out, void* stream);
 
 /* Counters the bench reports: kernels launched by this handle since creation. */
 int64_t pgtt_launch_count(pgtt_env* env);
-/* Which fused step kernel this handle launches: 0 = warp-per-env (pgtt_env_kernel), 1 = quad-per-env (pgtt_quad_kernel).
+/* Which physics kernel this handle launches: 0 = warp-per-env (pgtt_env_kernel), 1 = quad-per-env (pgtt_quad_kernel).
  * Chosen at creation from num_envs (measured crossover) or PGTT_KERNEL=warp|quad. */
 int pgtt_step_kernel_generation(pgtt_env* env);
 
@@ -174,17 +182,19 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
                     float* action, float* raw_action, float* log_prob, float* logits, void* stream);
 int64_t pgtt_policy_launch_count(pgtt_policy* p);
 
-/* One launch that files the current step's results into a time-major rollout slot: obs_state_dst / obs_priv_dst
- * <- obs (next_observation), reward_dst <- reward, discount_dst <- 1 - done, truncation_dst <- truncation.
+/* Copies the CURRENT observation / reward / done of the handle into a time-major rollout slot (device-to-device copies;
+ * used for slot 0 of an unroll - the per-step slots are written by pgtt_step_record): obs_state_dst / obs_priv_dst <- obs,
+ * reward_dst <- reward, discount_dst <- 1 - done, truncation_dst <- truncation.
  * All DEVICE pointers to ONE slot ([num_envs][dim]); any may be NULL. */
 int pgtt_record(pgtt_env* env, float* obs_state_dst, float* obs_priv_dst, float* reward_dst, float* discount_dst, float* truncation_dst,
                 void* stream);
 
-/* brax generate_unroll (training/train.py:135-161,242-263): T x (policy act -> wrapped env step -> record), all
- * launches issued natively on `stream` (3 kernels per control step, nothing returns to the host in between).
+/* brax generate_unroll (training/train.py:135-161,242-263): T x (policy act -> wrapped env step that records its own
+ * transition), all launches issued natively on `stream` (3 kernels per control step: policy, physics, task; nothing
+ * returns to the host in between).
  * Buffers are DEVICE, time-major: obs_* [T + 1][N][dim] (slot 0 = the observation the unroll starts from, so
  * next_observation[t] = observation[t + 1]); action / raw_action [T][N][12]; log_prob / reward / discount /
- * truncation [T][N]. Internal exploration noise is keyed by (seed, step0 + t). The 1 + 3 T launches are captured into a
+ * truncation [T][N]. Internal exploration noise is keyed by (seed, step0 + t). The 3 T launches (+ the slot-0 copies) are captured into a
  * CUDA graph on first use (per env / buffers / T) and replayed on an internal stream ordered after and before the
  * caller's stream (PGTT_ROLLOUT_GRAPH=0 issues them directly). */
 typedef struct {

@@ -184,6 +184,7 @@ def declare(lib):
     lib.pgtt_randomize.argtypes = [vp, vp, C.c_int, vp]
     lib.pgtt_reset.argtypes = [vp, vp, vp]
     lib.pgtt_step.argtypes = [vp, vp, C.c_int, vp]
+    lib.pgtt_step_record.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.pgtt_forward.argtypes = [vp, vp]
     lib.pgtt_heightscan.argtypes = [vp, vp, vp, vp, vp]
     lib.pgtt_get_buffers.argtypes = [vp, C.POINTER(Buffers)]
@@ -211,7 +212,7 @@ def declare(lib):
 
 ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
-    "pgtt_reset", "pgtt_step", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
+    "pgtt_reset", "pgtt_step", "pgtt_step_record", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act",
     "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_ppo_head", "pgtt_adam_clip", "pgtt_adam_scratch_floats",
 ]

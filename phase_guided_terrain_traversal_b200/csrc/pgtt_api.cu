@@ -106,7 +106,7 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
 // ----------------------------------------------------------------------------------------------
 // kernels / launch shims
 // ----------------------------------------------------------------------------------------------
-enum { OP_STEP = 0, OP_RESET, OP_FORWARD, OP_SCAN, OP_DEBUG };
+enum { OP_STEP = 0, OP_RESET, OP_FORWARD, OP_DEBUG, OP_TASK, OP_SCAN };   // OP_TASK / OP_SCAN run in the task kernel
 struct LaunchArgs {
   EnvBuffers B;
   int op, wrapped;
@@ -115,15 +115,19 @@ struct LaunchArgs {
   const float* center;
   const float* yaw;
   float* out;
+  RecordSlot rec;
 };
+#define TASK_BYTES ((sizeof(TaskWS) + 15) / 16 * 16)
+#define TASK_WARPS 8   // warps (= envs) per CTA of the task kernel
 
-DEV void dispatch(WS& w, const LaunchArgs& a, int env, int lane) {
+DEV void dispatch(WS& w, TaskWS& t, const LaunchArgs& a, int env, int lane) {
   switch (a.op) {
-    case OP_STEP: env_step(w, a.B, a.action, env, lane, a.wrapped); break;
-    case OP_RESET: env_reset(w, a.B, a.keys, env, lane); break;
+    case OP_STEP: env_physics(w, a.B, a.action, env, lane); break;
+    case OP_RESET: env_reset(w, t, a.B, a.keys, env, lane); break;
     case OP_FORWARD: env_forward(w, a.B, env, lane); break;
-    case OP_SCAN: env_scan(w, a.B, a.center, a.yaw, a.out, env, lane); break;
     case OP_DEBUG: env_debug_forward(w, a.B, a.out, env, lane); break;
+    case OP_TASK: task_step(t, a.B, a.action, env, lane, a.wrapped, a.rec); break;
+    case OP_SCAN: task_scan(t, a.B, a.center, a.yaw, a.out, env, lane); break;
   }
 }
 
@@ -134,6 +138,7 @@ DEV void dispatch(WS& w, const LaunchArgs& a, int env, int lane) {
     if (e_ != cudaSuccess) return fail(PGTT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// generation-1 physics / reset kernels: one warp per env, workspace in shared memory (reset also carries a TaskWS per warp)
 template <int OP>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 1) pgtt_env_kernel(LaunchArgs a) {
   extern __shared__ float4 smem4[];
@@ -147,15 +152,16 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 1) pgtt_env_kernel(L
     if (lane == 0) w.bar_threads = 32 * (live < wpb ? live : wpb);
     syncwarp();
   }
-  if (OP == OP_STEP) env_step(w, a.B, a.action, env, lane, a.wrapped);
-  else if (OP == OP_RESET) env_reset(w, a.B, a.keys, env, lane);
+  if (OP == OP_STEP) env_physics(w, a.B, a.action, env, lane);
+  else if (OP == OP_RESET) {
+    TaskWS& t = *reinterpret_cast<TaskWS*>(reinterpret_cast<char*>(smem4) + (size_t)wpb * WS_BYTES + (size_t)warp * TASK_BYTES);
+    env_reset(w, t, a.B, a.keys, env, lane);
+  }
   else if (OP == OP_FORWARD) env_forward(w, a.B, env, lane);
-  else if (OP == OP_SCAN) env_scan(w, a.B, a.center, a.yaw, a.out, env, lane);
   else env_debug_forward(w, a.B, a.out, env, lane);
 }
 
-// generation-2 kernels: one warp per CTA, eight envs per warp (pgtt_quad.cuh). No CTA-level cooperation, so the
-// grid is simply ceil(N / 8) single-warp CTAs: 4096 envs -> 512 warps over the 592 warp schedulers of 148 SMs.
+// generation-2 physics kernels: eight envs per warp (pgtt_quad.cuh), grid = ceil(N / 8) warps in CTAs of qw warps
 #define QWARPS_MAX 8
 template <int OP>
 __global__ void __launch_bounds__(32 * QWARPS_MAX) pgtt_quad_kernel(LaunchArgs a) {
@@ -164,23 +170,25 @@ __global__ void __launch_bounds__(32 * QWARPS_MAX) pgtt_quad_kernel(LaunchArgs a
   QShared& sh = *reinterpret_cast<QShared*>(reinterpret_cast<char*>(smem4) + (size_t)warp * ((sizeof(QShared) + 15) / 16 * 16));
   q_stage_consts(sh, lane);
   const int env = (blockIdx.x * (blockDim.x >> 5) + warp) * QENV + (lane >> 2);
-  if (OP == OP_STEP) q_env_step(sh, a.B, a.action, env, lane, a.wrapped);
+  if (OP == OP_STEP) q_env_physics(sh, a.B, a.action, env, lane);
   else q_env_debug_forward(sh, a.B, a.out, env, lane);
 }
 
-// transition write-out: one HBM-bound launch per control step (obs 171 + 215 floats, 3 scalars per env)
-__global__ void pgtt_record_kernel(EnvBuffers B, float* __restrict__ os, float* __restrict__ op, float* __restrict__ rw, float* __restrict__ dc,
-                                   float* __restrict__ tr) {
-  const size_t n_os = (size_t)B.N * GC.nobs, n_op = (size_t)B.N * GC.npriv, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_op; i += stride) {
-    if (op) op[i] = B.obs_priv[i];
-    if (os && i < n_os) os[i] = B.obs_state[i];
-    if (i < (size_t)B.N) {
-      if (rw) rw[i] = B.reward[i];
-      if (dc) dc[i] = 1.0f - B.done[i];
-      if (tr) tr[i] = B.truncation[i];
-    }
-  }
+// task kernel (pgtt_task.cuh): one warp per env, TASK_WARPS envs per CTA
+template <int OP>
+__global__ void __launch_bounds__(32 * TASK_WARPS) pgtt_task_kernel(LaunchArgs a) {
+  extern __shared__ float4 smem4[];
+  const int warp = warp_index(), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * TASK_WARPS + warp;
+  if (env >= a.B.N) return;
+  TaskWS& t = *reinterpret_cast<TaskWS*>(reinterpret_cast<char*>(smem4) + (size_t)warp * TASK_BYTES);
+  if (OP == OP_TASK) task_step(t, a.B, a.action, env, lane, a.wrapped, a.rec);
+  else task_scan(t, a.B, a.center, a.yaw, a.out, env, lane);
+}
+
+__global__ void pgtt_discount_kernel(const float* __restrict__ done, float* __restrict__ dc, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dc[i] = 1.0f - done[i];
 }
 
 __global__ void pgtt_randomize_kernel(EnvBuffers B, const uint32_t* keys, int dyn) {
@@ -190,38 +198,50 @@ __global__ void pgtt_randomize_kernel(EnvBuffers B, const uint32_t* keys, int dy
 #else
 ModelConst g_mc;
 #define CUDA_OK(call) do { (void)0; } while (0)
-struct WarpJob { const LaunchArgs* a; int env; WS* w; };
+struct WarpJob { const LaunchArgs* a; int env; WS* w; TaskWS* t; };
 static void warp_entry(void* p, int lane) {
   WarpJob* j = (WarpJob*)p;
-  dispatch(*j->w, *j->a, j->env, lane);
+  dispatch(*j->w, *j->t, *j->a, j->env, lane);
 }
 struct QuadJob { const LaunchArgs* a; int env0; QShared* sh; };
 static void quad_entry(void* p, int lane) {
   QuadJob* j = (QuadJob*)p;
   q_stage_consts(*j->sh, lane);
   const int env = j->env0 + (lane >> 2);
-  if (j->a->op == OP_STEP) q_env_step(*j->sh, j->a->B, j->a->action, env, lane, j->a->wrapped);
+  if (j->a->op == OP_STEP) q_env_physics(*j->sh, j->a->B, j->a->action, env, lane);
   else q_env_debug_forward(*j->sh, j->a->B, j->a->out, env, lane);
 }
 #endif
 
 struct pgtt_env {
   int device, N, wpb;
-  int quad;   // 1: generation-2 quad-per-env kernels for step / debug-forward (default), 0: warp-per-env (PGTT_KERNEL=warp)
+  int quad;   // 1: generation-2 quad-per-env physics kernel for step / debug-forward, 0: warp-per-env (PGTT_KERNEL=warp|quad overrides)
   ModelConst mc;
   EnvBuffers B;
   std::vector<void*> allocs;
   float* terrain_dev;
   int n_terrains;
   int64_t launches;
+  uint64_t serial;   // unique per pgtt_create (graph caches key on it: a freed handle's address can be re-used)
   bool randomized;
 };
 
-// The model / task constants live in __constant__ memory (one copy per device): the handle whose constants are resident is
-// tracked per device, and switching handles first drains the device so that a still-running kernel of the previous owner
-// never sees the new table.
+// The model / task constants live in __constant__ memory (one table per device). The handle whose constants are resident is
+// tracked per device; when another handle launches, the table is replaced by a STREAM-ORDERED copy on the launching stream
+// that first waits (device side, cudaStreamWaitEvent) for the last launch of the previous owner - so two handles on one
+// device (a training and an evaluation env, training/train.py:242-263) alternate without any host synchronisation.
+// Events are only recorded once a second handle exists on the device (its creation drains the device once).
 #define PGTT_MAX_DEVICES 64
-static pgtt_env* g_const_owner[PGTT_MAX_DEVICES] = {nullptr};
+struct DeviceConsts {
+  pgtt_env* owner = nullptr;
+  int handles = 0;
+#ifndef PGTT_HOST_EMU
+  cudaEvent_t last = nullptr;   // after the most recent launch of `owner`
+  bool have_last = false;
+#endif
+};
+static DeviceConsts g_dev[PGTT_MAX_DEVICES];
+static DeviceConsts& dev_consts(const pgtt_env* e) { return g_dev[e->device >= 0 && e->device < PGTT_MAX_DEVICES ? e->device : 0]; }
 
 static void* dev_alloc(pgtt_env* e, size_t bytes) {
   void* p = nullptr;
@@ -235,50 +255,75 @@ static void* dev_alloc(pgtt_env* e, size_t bytes) {
   return p;
 }
 
-static int upload_consts(pgtt_env* e) {
-  const int slot = e->device >= 0 && e->device < PGTT_MAX_DEVICES ? e->device : 0;
-  if (g_const_owner[slot] == e) return 0;
+// make e's constant table the resident one for launches on `stream` (no host synchronisation)
+static int make_resident(pgtt_env* e, void* stream) {
+  DeviceConsts& d = dev_consts(e);
+  if (d.owner == e) return 0;
 #ifndef PGTT_HOST_EMU
+  cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaSetDevice(e->device));
-  CUDA_OK(cudaDeviceSynchronize());
-  CUDA_OK(cudaMemcpyToSymbol(g_mc, &e->mc, sizeof(ModelConst)));
+  if (d.have_last) CUDA_OK(cudaStreamWaitEvent(st, d.last, 0));
+  CUDA_OK(cudaMemcpyToSymbolAsync(g_mc, &e->mc, sizeof(ModelConst), 0, cudaMemcpyHostToDevice, st));
 #else
+  (void)stream;
   g_mc = e->mc;
 #endif
-  g_const_owner[slot] = e;
+  d.owner = e;
+  return 0;
+}
+// after the launches of one entry point: lets the next owner order itself behind them
+static int mark_launched(pgtt_env* e, void* stream) {
+#ifndef PGTT_HOST_EMU
+  DeviceConsts& d = dev_consts(e);
+  if (d.handles > 1) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {   // a capturing stream gets its record from pgtt_internal_mark_launched after the replay
+      if (!d.last) CUDA_OK(cudaEventCreateWithFlags(&d.last, cudaEventDisableTiming));
+      CUDA_OK(cudaEventRecord(d.last, st));
+      d.have_last = true;
+    }
+  }
+#else
+  (void)e; (void)stream;
+#endif
   return 0;
 }
 
 static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
-  if (int rc = upload_consts(e)) return rc;
+  if (int rc = make_resident(e, stream)) return rc;
   a.B = e->B;
+  const bool task = a.op == OP_TASK || a.op == OP_SCAN;
 #ifndef PGTT_HOST_EMU
   cudaStream_t st = (cudaStream_t)stream;
-  if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
-    int qw = e->N >= 5000 ? QWARPS_MAX : 1;   // lockstep CTAs once there is more than one warp per scheduler
+  if (task) {
+    const int blocks = (e->N + TASK_WARPS - 1) / TASK_WARPS;
+    const size_t smem = TASK_WARPS * TASK_BYTES;
+    if (a.op == OP_TASK) pgtt_task_kernel<OP_TASK><<<blocks, 32 * TASK_WARPS, smem, st>>>(a);
+    else pgtt_task_kernel<OP_SCAN><<<blocks, 32 * TASK_WARPS, smem, st>>>(a);
+  } else if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
+    int qw = e->N >= 5000 ? QWARPS_MAX : 2;   // lockstep CTAs once there is more than one warp per scheduler
     if (const char* s = getenv("PGTT_QUAD_WARPS")) { const int v = atoi(s); if (v >= 1 && v <= QWARPS_MAX) qw = v; }
     const int qwarps = (e->N + QENV - 1) / QENV, qblocks = (qwarps + qw - 1) / qw;
     const size_t qsmem = qw * ((sizeof(QShared) + 15) / 16 * 16);
     if (a.op == OP_STEP) pgtt_quad_kernel<OP_STEP><<<qblocks, 32 * qw, qsmem, st>>>(a);
     else pgtt_quad_kernel<OP_DEBUG><<<qblocks, 32 * qw, qsmem, st>>>(a);
-    CUDA_OK(cudaGetLastError());
-    e->launches++;
-    return 0;
-  }
-  const int wpb = e->wpb;
-  const int blocks = (e->N + wpb - 1) / wpb;
-  const size_t smem = wpb * WS_BYTES;
-  switch (a.op) {
-    case OP_STEP: pgtt_env_kernel<OP_STEP><<<blocks, wpb * 32, smem, st>>>(a); break;
-    case OP_RESET: pgtt_env_kernel<OP_RESET><<<blocks, wpb * 32, smem, st>>>(a); break;
-    case OP_FORWARD: pgtt_env_kernel<OP_FORWARD><<<blocks, wpb * 32, smem, st>>>(a); break;
-    case OP_SCAN: pgtt_env_kernel<OP_SCAN><<<blocks, wpb * 32, smem, st>>>(a); break;
-    default: pgtt_env_kernel<OP_DEBUG><<<blocks, wpb * 32, smem, st>>>(a); break;
+  } else {
+    const int wpb = e->wpb;
+    const int blocks = (e->N + wpb - 1) / wpb;
+    const size_t smem = wpb * WS_BYTES;
+    switch (a.op) {
+      case OP_STEP: pgtt_env_kernel<OP_STEP><<<blocks, wpb * 32, smem, st>>>(a); break;
+      case OP_RESET: pgtt_env_kernel<OP_RESET><<<blocks, wpb * 32, smem + wpb * TASK_BYTES, st>>>(a); break;
+      case OP_FORWARD: pgtt_env_kernel<OP_FORWARD><<<blocks, wpb * 32, smem, st>>>(a); break;
+      default: pgtt_env_kernel<OP_DEBUG><<<blocks, wpb * 32, smem, st>>>(a); break;
+    }
   }
   CUDA_OK(cudaGetLastError());
 #else
   (void)stream;
-  if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
+  if (!task && e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
     const int nwarps = (e->N + QENV - 1) / QENV;
 #pragma omp parallel
     {
@@ -291,19 +336,21 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
       }
       free(sh);
     }
-    e->launches++;
-    return 0;
-  }
+  } else {
 #pragma omp parallel
-  {
-    WS* w = (WS*)aligned_alloc(16, WS_BYTES);
+    {
+      WS* w = (WS*)aligned_alloc(16, WS_BYTES);
+      TaskWS* t = (TaskWS*)aligned_alloc(16, TASK_BYTES);
 #pragma omp for schedule(dynamic, 1)
-    for (int env = 0; env < e->N; env++) {
-      memset(w, 0xCD, WS_BYTES);  // poison: uninitialised reads show up as garbage, like on the GPU
-      WarpJob j = {&a, env, w};
-      emu_run_warp(warp_entry, &j);
+      for (int env = 0; env < e->N; env++) {
+        memset(w, 0xCD, WS_BYTES);  // poison: uninitialised reads show up as garbage, like on the GPU
+        memset(t, 0xCD, TASK_BYTES);
+        WarpJob j = {&a, env, w, t};
+        emu_run_warp(warp_entry, &j);
+      }
+      free(w);
+      free(t);
     }
-    free(w);
   }
 #endif
   e->launches++;
@@ -340,9 +387,8 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
     CUDA_OK(cudaSetDevice(device));
     const size_t smem = MAX_WARPS_PER_BLOCK * WS_BYTES;
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + MAX_WARPS_PER_BLOCK * TASK_BYTES)));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t qsmem = QWARPS_MAX * ((sizeof(QShared) + 15) / 16 * 16);
     CUDA_OK(cudaFuncSetAttribute(pgtt_quad_kernel<OP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
@@ -350,6 +396,14 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   }
 #endif
   pgtt_env* e = new pgtt_env();
+  {
+    DeviceConsts& d = g_dev[device >= 0 && device < PGTT_MAX_DEVICES ? device : 0];
+    d.handles++;
+#ifndef PGTT_HOST_EMU
+    if (d.handles == 2) cudaDeviceSynchronize();   // launches of the first handle were not followed by event records so far
+#endif
+  }
+  { static uint64_t next_serial = 1; e->serial = next_serial++; }
   e->device = device; e->N = num_envs; e->wpb = pick_warps_per_block(num_envs); e->terrain_dev = nullptr; e->n_terrains = 0; e->launches = 0; e->randomized = false;
   // Kernel generation for step / debug-forward. Measured on B200 (profiles/r01c): the quad kernel needs ~0.7 ms per
   // step up to 8192 envs (one or two latency-bound warps per scheduler) and the warp-per-env kernel 0.125 us per env,
@@ -395,7 +449,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   for (int i = 0; i < 5; i++) c.lim_solimp[i] = (float)m->jnt_solimp[i];
   for (int a = 0; a < 12; a++) {
     const int hinge = m->act_dof[a] - 6;
-    if (hinge < 0 || hinge >= 12) { delete e; return fail(PGTT_ERR_ARG, "pgtt_create: actuator must drive a hinge"); }
+    if (hinge < 0 || hinge >= 12) { pgtt_destroy(e); return fail(PGTT_ERR_ARG, "pgtt_create: actuator must drive a hinge"); }
     c.hinge_of_act[a] = hinge; c.act_of_hinge[hinge] = a;
     c.nom_gain[a] = (float)m->act_gain[a]; c.act_bias0[a] = (float)m->act_bias[a][0]; c.nom_bias1[a] = (float)m->act_bias[a][1];
     c.act_bias2[a] = (float)m->act_bias[a][2];
@@ -466,7 +520,11 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
 
 int pgtt_destroy(pgtt_env* e) {
   if (!e) return PGTT_OK;
-  for (int i = 0; i < PGTT_MAX_DEVICES; i++) if (g_const_owner[i] == e) g_const_owner[i] = nullptr;
+  {
+    DeviceConsts& d = dev_consts(e);
+    if (d.owner == e) d.owner = nullptr;
+    if (d.handles > 0) d.handles--;
+  }
 #ifndef PGTT_HOST_EMU
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
@@ -525,10 +583,11 @@ int pgtt_set_terrain_table(pgtt_env* e, const float* boxes, int T) {
 int pgtt_randomize(pgtt_env* e, const uint32_t* keys, int dynamics, void* stream) {
   if (!e || !keys) return fail(PGTT_ERR_ARG, "pgtt_randomize: null argument");
   if (e->mc.n_boxes > 0 && !e->terrain_dev) return fail(PGTT_ERR_STATE, "pgtt_randomize: stairs task needs pgtt_set_terrain_table first");
-  if (int rc = upload_consts(e)) return rc;
+  if (int rc = make_resident(e, stream)) return rc;
 #ifndef PGTT_HOST_EMU
   pgtt_randomize_kernel<<<(e->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->B, keys, dynamics);
   CUDA_OK(cudaGetLastError());
+  if (int rc = mark_launched(e, stream)) return rc;
 #else
   (void)stream;
 #pragma omp parallel for
@@ -551,22 +610,32 @@ int pgtt_reset(pgtt_env* e, const uint32_t* keys, void* stream) {
   if (!keys) return fail(PGTT_ERR_ARG, "pgtt_reset: null keys");
   LaunchArgs a; memset(&a, 0, sizeof(a));
   a.op = OP_RESET; a.keys = keys;
-  return launch(e, a, stream);
+  if (int rc = launch(e, a, stream)) return rc;
+  return mark_launched(e, stream);
 }
 
-int pgtt_step(pgtt_env* e, const float* action, int wrapped, void* stream) {
+int pgtt_step_record(pgtt_env* e, const float* action, int wrapped, float* os, float* op, float* rw, float* dc, float* tr, void* stream) {
   if (int rc = check_ready(e, "pgtt_step")) return rc;
   if (!action) return fail(PGTT_ERR_ARG, "pgtt_step: null action");
   LaunchArgs a; memset(&a, 0, sizeof(a));
   a.op = OP_STEP; a.action = action; a.wrapped = wrapped;
-  return launch(e, a, stream);
+  a.rec.obs_state = os; a.rec.obs_priv = op; a.rec.reward = rw; a.rec.discount = dc; a.rec.truncation = tr;
+  if (int rc = launch(e, a, stream)) return rc;   // physics: n_substeps x mjx.step
+  a.op = OP_TASK;
+  if (int rc = launch(e, a, stream)) return rc;   // task layer, wrappers, transition slot
+  return mark_launched(e, stream);
+}
+
+int pgtt_step(pgtt_env* e, const float* action, int wrapped, void* stream) {
+  return pgtt_step_record(e, action, wrapped, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int pgtt_forward(pgtt_env* e, void* stream) {
   if (int rc = check_ready(e, "pgtt_forward")) return rc;
   LaunchArgs a; memset(&a, 0, sizeof(a));
   a.op = OP_FORWARD;
-  return launch(e, a, stream);
+  if (int rc = launch(e, a, stream)) return rc;
+  return mark_launched(e, stream);
 }
 
 int pgtt_heightscan(pgtt_env* e, const float* center, const float* yaw, float* out, void* stream) {
@@ -574,7 +643,8 @@ int pgtt_heightscan(pgtt_env* e, const float* center, const float* yaw, float* o
   if (!center || !yaw || !out) return fail(PGTT_ERR_ARG, "pgtt_heightscan: null argument");
   LaunchArgs a; memset(&a, 0, sizeof(a));
   a.op = OP_SCAN; a.center = center; a.yaw = yaw; a.out = out;
-  return launch(e, a, stream);
+  if (int rc = launch(e, a, stream)) return rc;
+  return mark_launched(e, stream);
 }
 
 int pgtt_debug_forward(pgtt_env* e, float* out, void* stream) {
@@ -582,7 +652,8 @@ int pgtt_debug_forward(pgtt_env* e, float* out, void* stream) {
   if (!out) return fail(PGTT_ERR_ARG, "pgtt_debug_forward: null out");
   LaunchArgs a; memset(&a, 0, sizeof(a));
   a.op = OP_DEBUG; a.out = out;
-  return launch(e, a, stream);
+  if (int rc = launch(e, a, stream)) return rc;
+  return mark_launched(e, stream);
 }
 
 int pgtt_get_buffers(pgtt_env* e, pgtt_buffers* o) {
@@ -619,20 +690,29 @@ int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
 // graph replays of the rollout launch this handle's kernels without going through launch(): keep the counter honest
 void pgtt_internal_count_launches(pgtt_env* e, int64_t n) { if (e) e->launches += n; }
 
+uint64_t pgtt_internal_serial(pgtt_env* e) { return e ? e->serial : 0; }
+int pgtt_internal_make_resident(pgtt_env* e, void* stream) { return e ? make_resident(e, stream) : PGTT_OK; }
+int pgtt_internal_mark_launched(pgtt_env* e, void* stream) { return e ? mark_launched(e, stream) : PGTT_OK; }
+
+// Files the CURRENT observation / reward / done into a rollout slot with plain device copies (the per-step slots of an
+// unroll are written by the task kernel itself, pgtt_step_record; this entry point fills slot 0 of an unroll).
 int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* tr, void* stream) {
   if (!e) return fail(PGTT_ERR_ARG, "pgtt_record: null handle");
-  if (int rc = upload_consts(e)) return rc;
   const EnvBuffers& B = e->B;
+  const size_t N = (size_t)B.N;
 #ifndef PGTT_HOST_EMU
-  const size_t n = (size_t)B.N * e->mc.npriv;
-  const int threads = 256;
-  size_t blocks = (n + threads - 1) / threads;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  pgtt_record_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(B, os, op, rw, dc, tr);
-  CUDA_OK(cudaGetLastError());
+  cudaStream_t st = (cudaStream_t)stream;
+  if (os) CUDA_OK(cudaMemcpyAsync(os, B.obs_state, N * e->mc.nobs * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (op) CUDA_OK(cudaMemcpyAsync(op, B.obs_priv, N * e->mc.npriv * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (rw) CUDA_OK(cudaMemcpyAsync(rw, B.reward, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (tr) CUDA_OK(cudaMemcpyAsync(tr, B.truncation, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (dc) {
+    pgtt_discount_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(B.done, dc, (int)N);
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+  }
 #else
   (void)stream;
-  const size_t N = (size_t)B.N;
   if (os) memcpy(os, B.obs_state, N * e->mc.nobs * sizeof(float));
   if (op) memcpy(op, B.obs_priv, N * e->mc.npriv * sizeof(float));
   for (size_t i = 0; i < N; i++) {
@@ -641,7 +721,6 @@ int pgtt_record(pgtt_env* e, float* os, float* op, float* rw, float* dc, float* 
     if (tr) tr[i] = B.truncation[i];
   }
 #endif
-  e->launches++;
   return PGTT_OK;
 }
 

@@ -28,7 +28,11 @@
 
 #include "../../include/pgtt_b200.h"
 
-extern "C" void pgtt_internal_count_launches(pgtt_env* env, int64_t n);   // pgtt_api.cu (not part of the ABI header)
+// pgtt_api.cu (not part of the ABI header)
+extern "C" void pgtt_internal_count_launches(pgtt_env* env, int64_t n);
+extern "C" int pgtt_internal_make_resident(pgtt_env* env, void* stream);
+extern "C" int pgtt_internal_mark_launched(pgtt_env* env, void* stream);
+extern "C" uint64_t pgtt_internal_serial(pgtt_env* env);   // unique per pgtt_create: a handle re-created at the same address is a different env
 
 #define POL_TM 128            // envs per CTA = MMA M
 #define POL_MAXK 512          // widest activation
@@ -571,7 +575,7 @@ struct pgtt_policy {
   cudaStream_t gstream;
   cudaEvent_t ev_in, ev_out;
   cudaGraphExec_t gexec;
-  struct { pgtt_env* env; int T, deterministic; uint64_t seed; pgtt_rollout_buffers o; } gkey;
+  struct { pgtt_env* env; uint64_t env_serial; int T, deterministic; uint64_t seed; pgtt_rollout_buffers o; } gkey;
   int use_graph;
   __nv_bfloat16* w_dev;
   float *bias_dev, *mean_dev, *istd_dev;
@@ -910,11 +914,11 @@ static int rollout_issue(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, 
     if (int rc = pgtt_policy_act(pol, o->obs_state + (size_t)t * N * nobs, (int)N, seed, step0 + (uint64_t)t, deterministic, nullptr, act,
                                  o->raw_action ? o->raw_action + (size_t)t * N * A : nullptr, o->log_prob ? o->log_prob + (size_t)t * N : nullptr,
                                  nullptr, stream)) return rc;
-    if (int rc = pgtt_step(env, act, 1, stream)) return pfail(rc, pgtt_last_error());
-    if (int rc = pgtt_record(env, o->obs_state + (size_t)(t + 1) * N * nobs,
-                             o->obs_privileged ? o->obs_privileged + (size_t)(t + 1) * N * npriv : nullptr,
-                             o->reward ? o->reward + (size_t)t * N : nullptr, o->discount ? o->discount + (size_t)t * N : nullptr,
-                             o->truncation ? o->truncation + (size_t)t * N : nullptr, stream)) return pfail(rc, pgtt_last_error());
+    // the task kernel of the step writes the transition slot itself
+    if (int rc = pgtt_step_record(env, act, 1, o->obs_state + (size_t)(t + 1) * N * nobs,
+                                  o->obs_privileged ? o->obs_privileged + (size_t)(t + 1) * N * npriv : nullptr,
+                                  o->reward ? o->reward + (size_t)t * N : nullptr, o->discount ? o->discount + (size_t)t * N : nullptr,
+                                  o->truncation ? o->truncation + (size_t)t * N : nullptr, stream)) return pfail(rc, pgtt_last_error());
   }
   return PGTT_OK;
 }
@@ -941,12 +945,12 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t
     PCUDA(cudaEventCreateWithFlags(&pol->ev_out, cudaEventDisableTiming));
     PCUDA(cudaMalloc(&pol->step_dev, sizeof(unsigned long long)));
   }
-  const bool same = pol->gexec && pol->gkey.env == env && pol->gkey.T == T && pol->gkey.deterministic == deterministic && pol->gkey.seed == seed &&
+  const bool same = pol->gexec && pol->gkey.env == env && pol->gkey.env_serial == pgtt_internal_serial(env) && pol->gkey.T == T && pol->gkey.deterministic == deterministic && pol->gkey.seed == seed &&
                     memcmp(&pol->gkey.o, o, sizeof(*o)) == 0;
   if (!same) {
     if (pol->gexec) { cudaGraphExecDestroy(pol->gexec); pol->gexec = nullptr; }
-    // make sure this env's constant table is resident before capturing (an upload synchronises the device)
-    if (int rc = pgtt_record(env, nullptr, nullptr, nullptr, nullptr, nullptr, user)) return pfail(rc, pgtt_last_error());
+    // this env's constant table must be resident before the capture starts (the stream-ordered upload is not captured)
+    if (int rc = pgtt_internal_make_resident(env, user)) return pfail(rc, pgtt_last_error());
     PCUDA(cudaStreamSynchronize(user));
     cudaGraph_t graph = nullptr;
     pol->step_base_arg = pol->step_dev;
@@ -964,15 +968,18 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t
       pol->gexec = nullptr; pol->use_graph = 0;
       return rollout_issue(env, pol, T, seed, step0, deterministic, o, N, nobs, npriv, stream);
     }
-    pol->gkey.env = env; pol->gkey.T = T; pol->gkey.deterministic = deterministic; pol->gkey.seed = seed; pol->gkey.o = *o;
+    pol->gkey.env = env; pol->gkey.env_serial = pgtt_internal_serial(env); pol->gkey.T = T; pol->gkey.deterministic = deterministic; pol->gkey.seed = seed; pol->gkey.o = *o;
   } else {
-    pgtt_internal_count_launches(env, 1 + 2 * (int64_t)T);   // capture counted the first unroll's launches
+    pgtt_internal_count_launches(env, 2 * (int64_t)T);   // capture counted the first unroll's launches
     pol->launches += T;
   }
   PCUDA(cudaEventRecord(pol->ev_in, user));
   PCUDA(cudaStreamWaitEvent(pol->gstream, pol->ev_in, 0));
+  // another handle of this device may have run in between: its constant table is replaced (stream-ordered) before the replay
+  if (int rc = pgtt_internal_make_resident(env, pol->gstream)) return pfail(rc, pgtt_last_error());
   pgtt_set_u64_kernel<<<1, 1, 0, pol->gstream>>>(pol->step_dev, (unsigned long long)step0);
   PCUDA(cudaGraphLaunch(pol->gexec, pol->gstream));
+  if (int rc = pgtt_internal_mark_launched(env, pol->gstream)) return pfail(rc, pgtt_last_error());
   PCUDA(cudaEventRecord(pol->ev_out, pol->gstream));
   PCUDA(cudaStreamWaitEvent(user, pol->ev_out, 0));
   return PGTT_OK;

@@ -49,9 +49,6 @@ struct LegC {
 
 struct QShared {
   LegC leg[4];
-  float scan[QENV][NRAY];
-  int boxlist[QENV][NBOX];
-  int nlist[QENV];
   // lane-private columns ([k][lane]: conflict-free, no synchronisation needed)
   float cand_dist[QCAND][32], cand_cd2[QCAND][32];
   int cand_box[QCAND][32], cand_rank[QCAND][32];
@@ -1278,155 +1275,6 @@ DEV void q_forward(QFwd& O, QSol& S, QSens& Z, QNear& Nr, bool build_near, QShar
   if (sens) q_sensors_post(Z, S.qacc);
 }
 
-// ----------------------------------------------------------------------------------------------
-// create_sensor_matrix (go2/heightmap.py:25-67) for the env of this quad: 117 vertical rays, lane g casts rays
-// g, g+4, ...; the near-box list is built by the four lanes with one ballot per four boxes
-// ----------------------------------------------------------------------------------------------
-DEV void q_heightscan(QShared& Sh, const QModel& M, float cx, float cyy, float cz, float yaw, float* out, int slot, int g, int qbase) {
-  float sy, cy;
-  sincos_(yaw, &sy, &cy);
-  const float oz = cz + 0.6f;
-  const int nb = GC.n_boxes;
-  const float4* bp = reinterpret_cast<const float4*>(M.box);
-  int nl = 0;
-  if (nb > 0) {
-    const unsigned lt = (1u << g) - 1u;
-    constexpr int HCH = 5;   // five boxes per lane per round trip to L2 (see q_build_near)
-    static_assert(((NBOX + 3) / 4) % HCH == 0, "chunking of the heightscan list build");
-#pragma unroll 1
-    for (int it0 = 0; it0 < (NBOX + 3) / 4; it0 += HCH) {
-      float4 c0[HCH], c1[HCH];
-#pragma unroll
-      for (int u = 0; u < HCH; u++) {
-        const int k = (it0 + u) * 4 + g, kc = k < nb ? k : nb - 1;
-        c0[u] = ldg4(bp + 2 * kc); c1[u] = ldg4(bp + 2 * kc + 1);
-      }
-#pragma unroll
-      for (int u = 0; u < HCH; u++) {
-        const int k = (it0 + u) * 4 + g;
-        bool near = false;
-        if (k < nb) {
-          const float4 b0 = c0[u], b1 = c1[u];
-          const float dx = b0.x - cx, dy = b0.y - cyy;
-          const float rad = sqrtf(b0.w * b0.w + b1.x * b1.x) + 0.75f;  // grid half-diagonal 0.7211 + slack
-          near = dx * dx + dy * dy <= rad * rad;
-        }
-        const unsigned nib = (wballot(near) >> qbase) & 0xFu;
-        if (near) Sh.boxlist[slot][nl + popc(nib & lt)] = k;
-        nl += popc(nib);
-      }
-    }
-    syncwarp();
-  }
-  // rays of this lane (r = g, g + 4, ...) stay in registers; the box loop is the OUTER loop so that each listed box is
-  // fetched once per lane instead of once per ray. Per (ray, box) pair the arithmetic is unchanged and min() does not
-  // depend on the order of the boxes: bit-identical to the ray-outer form.
-  constexpr int RPL = (NRAY + 3) / 4;
-  float ox[RPL], oy[RPL], best[RPL];
-#pragma unroll
-  for (int q = 0; q < RPL; q++) {
-    const int r = (g + 4 * q < NRAY) ? g + 4 * q : NRAY - 1;
-    const int i = r / NRAY_W, j = r % NRAY_W;
-    const float p = (6.0f - (float)i) * 0.1f, k = (4.0f - (float)j) * 0.1f;
-    ox[q] = cx + (p * cy - k * sy); oy[q] = cyy + (p * sy + k * cy);
-    if (i == 6 && j == 4) { ox[q] = cx; oy[q] = cyy; }
-    best[q] = Q_INF;
-    if (oz >= 0.f) best[q] = oz;  // floor plane z = 0
-  }
-#pragma unroll 1
-  for (int t = 0; t < nl; t++) {
-    const int kb = Sh.boxlist[slot][t];
-    const float4 b0 = ldg4(bp + 2 * kb), b1 = ldg4(bp + 2 * kb + 1);
-    const float lz = oz - b0.z;
-    const float ttop = lz - b1.y, tbot = lz + b1.y;
-#pragma unroll
-    for (int q = 0; q < RPL; q++) {
-      const float rx = ox[q] - b0.x, ry = oy[q] - b0.y;
-      const float lx = b1.z * rx + b1.w * ry, ly = -b1.w * rx + b1.z * ry;
-      if (fabsf(lx) <= b0.w && fabsf(ly) <= b1.x) {
-        if (ttop >= 0.f) best[q] = fminf(best[q], ttop);
-        else if (tbot >= 0.f) best[q] = fminf(best[q], tbot);
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < RPL; q++) {
-    const int r = g + 4 * q;
-    if (r < NRAY) {
-      const float z = oz - best[q];
-      if (out) { out[3 * r] = ox[q]; out[3 * r + 1] = oy[q]; out[3 * r + 2] = z; }
-      Sh.scan[slot][r] = z;
-    }
-  }
-  syncwarp();
-}
-
-// ----------------------------------------------------------------------------------------------
-// observation (joystick_pgtt.py:238-370); `rng` is advanced by the five splits of _get_obs.
-// kf = this lane's foot in sensor order (FR FL RR RL) = g ^ 1
-// ----------------------------------------------------------------------------------------------
-DEV void q_write_obs(const EnvBuffers& B, QShared& Sh, int env, int slot, int g, int qbase, Key& rng, const QSens& Z, const QState& X, const LegC& L,
-                     const float* actf, float phase_k, float gait_freq, const float* last_act3, float command_g, int last_contact_k, float air_k, bool ok) {
-  Key chain[5];
-#pragma unroll
-  for (int s = 0; s < 5; s++) { chain[s] = rng; rng = rng_split(rng, 2, 0); }
-  float* o = B.obs_state + (size_t)env * GC.nobs;
-  float* pr = B.obs_priv + (size_t)env * GC.npriv;
-  const float lvl = GC.noise_level;
-  const int kf = g ^ 1;
-  // layout: the baseline variant (go2/joystick.py:333-341) has no phase block and no gait_freq
-  const bool base_v = GC.variant != 0;
-  const int o_scan = base_v ? 30 : 38, o_last = base_v ? 147 : 156, o_cmd = base_v ? 159 : 168, px = GC.nobs;
-  {
-    const Key kgyro = rng_split(chain[0], 2, 1), kgrav = rng_split(chain[1], 2, 1), kpos = rng_split(chain[2], 2, 1), kvel = rng_split(chain[3], 2, 1);
-    if (g < 3 && ok) {
-      const float u0 = 2.f * rng_unit(kgyro, 3, g) - 1.f, u1 = 2.f * rng_unit(kgrav, 3, g) - 1.f;
-      const float v0 = Z.gyro[g < 3 ? g : 0] + u0 * lvl * GC.noise_gyro;
-      const float grav = -(g == 0 ? Z.Rb[6] : (g == 1 ? Z.Rb[7] : Z.Rb[8]));     // xmat^T (0,0,-1) = -(third row of R)
-      const float v1 = grav + u1 * lvl * GC.noise_gravity;
-      o[g] = v0; pr[g] = v0; o[3 + g] = v1; pr[3 + g] = v1;
-    }
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      const int idx = 3 * g + t;
-      const float up = 2.f * rng_unit(kpos, 12, idx) - 1.f, uv = 2.f * rng_unit(kvel, 12, idx) - 1.f;
-      const float vp = (X.ql[t] + up * lvl * GC.noise_joint_pos) - L.default_pose[t];
-      const float vv = X.vl[t] + uv * lvl * GC.noise_joint_vel;
-      if (ok) { o[6 + idx] = vp; pr[6 + idx] = vp; o[18 + idx] = vv; pr[18 + idx] = vv; }
-    }
-  }
-  const Key scan_key = rng_split(chain[4], 2, 1);   // the linvel key, re-used for the height scan (Q9)
-  {
-    float s, c;
-    sincos_(phase_k, &s, &c);
-    if (ok && !base_v) { o[30 + kf] = c; o[34 + kf] = s; pr[30 + kf] = c; pr[34 + kf] = s; }
-  }
-  float zmin = Q_INF;
-  for (int r = g; r < NRAY; r += 4) zmin = fminf(zmin, Sh.scan[slot][r]);
-  zmin = qmin(zmin);
-  for (int r = g; r < NRAY; r += 4) {
-    const float z = (Sh.scan[slot][r] - zmin) + (2.f * rng_unit(scan_key, NRAY, r) - 1.f) * lvl * GC.noise_heightscan;
-    if (ok) { o[o_scan + r] = z; pr[o_scan + r] = z; }
-  }
-  if (!ok) return;
-  if (g == 0 && !base_v) { o[155] = gait_freq; pr[155] = gait_freq; }
-#pragma unroll
-  for (int t = 0; t < 3; t++) {
-    const int idx = 3 * g + t;
-    o[o_last + idx] = last_act3[t]; pr[o_last + idx] = last_act3[t];
-    pr[px + 9 + L.act[t]] = actf[t];
-    pr[px + 25 + 3 * kf + t] = Z.fvel[t];
-  }
-  if (g < 3) {
-    o[o_cmd + g] = command_g; pr[o_cmd + g] = command_g;
-    const float ll = g == 0 ? Z.llin[0] : (g == 1 ? Z.llin[1] : Z.llin[2]);
-    const float ac = g == 0 ? Z.acc[0] : (g == 1 ? Z.acc[1] : Z.acc[2]);
-    const float ga = g == 0 ? Z.gang[0] : (g == 1 ? Z.gang[1] : Z.gang[2]);
-    pr[px + g] = ll; pr[px + 3 + g] = ac; pr[px + 6 + g] = ga; pr[px + 41 + g] = 0.f;
-  }
-  pr[px + 21 + kf] = (float)last_contact_k; pr[px + 37 + kf] = air_k;
-}
-
 // store the mjx.Data fields the task / API exposes
 DEV void q_store_data(const EnvBuffers& B, int env, int g, const QState& X, const QSol& S, const QSens& Z, const QFwd& O, const LegC& L, const float* ctrl3) {
   if (g == 0) {
@@ -1468,29 +1316,24 @@ DEV void q_store_data(const EnvBuffers& B, int env, int g, const QState& X, cons
 }
 
 // ----------------------------------------------------------------------------------------------
-// Joystick.step + training wrappers for the eight envs of a warp (semantics of pgtt_env.cuh:env_step)
+// mjx_env.step of Joystick.step (joystick_pgtt.py:145-148) for the eight envs of a warp: motor targets, n_substeps x
+// mjx.step; mjx.Data goes to the handle's buffers for the task kernel (pgtt_task.cuh)
 // ----------------------------------------------------------------------------------------------
-DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, int env_raw, int lane, int wrapped) {
-  const int g = lane & 3, qbase = lane & ~3, slot = lane >> 2, kf = g ^ 1;
+DEV void q_env_physics(QShared& Sh, const EnvBuffers& B, const float* action_all, int env_raw, int lane) {
+  const int g = lane & 3, qbase = lane & ~3;
   const bool ok = env_raw < B.N;
   const int env = ok ? env_raw : B.N - 1;          // surplus quads shadow the last env and store nothing
   const LegC& L = Sh.leg[g];
-  const float dt = GC.ctrl_dt;
   QModel M;
   QState X;
   q_load_model(M, B, L, env, g);
   q_load_state(X, B, env, g);
-  // BraxAutoResetWrapper.step: steps <- 0 where the previous step ended an episode; done cleared
-  float steps = 0.f;
-  if (wrapped) { steps = B.steps[env]; if (B.done[env] != 0.f) steps = 0.f; }
   const float* act = action_all + (size_t)env * NU;
-  float actA[3], mtA[3];   // action / motor target with array (actuator-order) index 3g+t; X.ctrl: of the actuator driving hinge t
 #pragma unroll
-  for (int t = 0; t < 3; t++) {
-    actA[t] = act[3 * g + t];
-    mtA[t] = GC.default_pose[3 * g + t] + actA[t] * GC.action_scale;
+  for (int t = 0; t < 3; t++) {   // motor target with array (actuator-order) index 3g+t; X.ctrl: of the actuator driving hinge t
+    const float mtA = GC.default_pose[3 * g + t] + act[3 * g + t] * GC.action_scale;
     X.ctrl[t] = L.mt_default[t] + act[L.act[t]] * GC.action_scale;
-    if (ok) B.motor_targets[env * NU + 3 * g + t] = mtA[t];
+    if (ok) B.motor_targets[env * NU + 3 * g + t] = mtA;
   }
   QFwd O;
   QSol S;
@@ -1509,226 +1352,13 @@ DEV void q_env_step(QShared& Sh, const EnvBuffers& B, const float* action_all, i
 #pragma unroll
     for (int t = 0; t < 3; t++) X.wl[t] = S.qacc.l[t];
   }
-  if (ok && g == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (i < nsub) B.solver_niter[env * 4 + i] = niter[i];
-  }
-  // compute_contact (base.py:153-171): any contact of this lane's foot with dist < 0 (flag order FR FL RR RL = kf)
-  int contact = O.GP.dist < 0.f;
-  {
-    const int xhit = (O.GX.box >= 0) && (O.GX.dist < 0.f);
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      const int lg = shfl(O.GX.leg, qbase | s), hit = shfl(xhit, qbase | s);
-      contact |= (hit && lg == g);
-    }
-  }
-  const int last_contact = B.last_contact[env * 4 + kf];
-  float air = B.feet_air_time[env * 4 + kf];
-  const int first_contact = (air > 0.f) && (contact | last_contact);
-  air += dt;
-  float swing_peak = fmaxf(B.swing_peak[env * 4 + kf], Z.fpos[2]);
-  // height scan at the post-step pose, quadrant statistics (joystick_pgtt.py:167-190, Q8)
-  q_heightscan(Sh, M, X.qb[0], X.qb[1], X.qb[2], quat_to_yaw(X.qb + 3), ok ? B.heightscan + (size_t)env * NRAY * 3 : nullptr, slot, g, qbase);
-  float hmax;
-  {
-    const int q = kf;   // foot kf reads quadrant kf
-    const int r0 = (q < 2) ? 0 : 7, r1 = (q < 2) ? 6 : 13, c0 = (q & 1) ? 0 : 7, c1 = (q & 1) ? 6 : 9;
-    float mx = -Q_INF, mn = Q_INF;
-    for (int r = r0; r < r1; r++)
-      for (int c = c0; c < c1; c++) { const float z = Sh.scan[slot][r * NRAY_W + c]; mx = fmaxf(mx, z); mn = fminf(mn, z); }
-    hmax = GC.variant ? mx : mx - mn;   // joystick.py:186 vs joystick_pgtt.py:189
-    if (ok) { B.H_max[env * 4 + kf] = hmax; B.H_min[env * 4 + kf] = mn; }
-  }
-  // observation (uses info BEFORE the bookkeeping below, except feet_air_time which is already += dt)
-  Key rng; rng.a = B.rng[env * 2]; rng.b = B.rng[env * 2 + 1];
-  const float phase = B.phase[env * 4 + kf];
-  float last_act[3];
-#pragma unroll
-  for (int t = 0; t < 3; t++) last_act[t] = B.last_act[env * NU + 3 * g + t];
-  const float cmd0 = B.command[env * 3], cmd1 = B.command[env * 3 + 1], cmd2 = B.command[env * 3 + 2];
-  const float command_g = g == 0 ? cmd0 : (g == 1 ? cmd1 : cmd2);
-  const int step = B.step[env];
-  const float gait_freq = B.gait_freq[env];
-  q_write_obs(B, Sh, env, slot, g, qbase, rng, Z, X, L, O.actf, phase, gait_freq, last_act, command_g, last_contact, air, ok);
-  if (ok && (step % GC.history_update_steps == 0)) {   // history rolls of _get_obs (joystick_pgtt.py:319-334)
-    float* qv = B.qvel_hist + (size_t)env * 24;
-    float* qe = B.qpos_err_hist + (size_t)env * 24;
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      const int i = 3 * g + t;
-      qv[12 + i] = qv[i]; qe[12 + i] = qe[i];
-      qv[i] = X.vl[t]; qe[i] = X.ql[t] - mtA[t];
-    }
-  }
-  // termination (joystick_pgtt.py:233-236) + failure guard (see pgtt_env.cuh:env_step): non-finite / absurd state ends the episode
-  bool bad = false;
-#pragma unroll
-  for (int i = 0; i < 7; i++) bad |= !(fabsf(X.qb[i]) < 1e6f);
-#pragma unroll
-  for (int i = 0; i < 6; i++) bad |= !(fabsf(X.vb[i]) < 1e6f);
-#pragma unroll
-  for (int t = 0; t < 3; t++) bad |= !(fabsf(X.ql[t]) < 1e6f) || !(fabsf(X.vl[t]) < 1e6f);
-  const bool poisoned = qany(bad, qbase);   // collective: every lane takes part
-  const int done = (Z.up[2] < 0.f) || poisoned;
-  // rewards (joystick_pgtt.py:372-599): per-joint / per-foot partials on the owning lane, summed over the quad
-  const float cmd_norm = sqrtf(cmd0 * cmd0 + cmd1 * cmd1 + cmd2 * cmd2);
-  float vals[15];
-#pragma unroll
-  for (int k = 0; k < 15; k++) vals[k] = 0.f;
-  // the energy term multiplies qvel[6 + i] (joint order) by actuator_force[i] (actuator order), as the reference does:
-  // fetch the force with ARRAY index 3g + t from the lane that owns its hinge
-  float afA[3];
-#pragma unroll
-  for (int t = 0; t < 3; t++) {
-    const int h = GC.hinge_of_act[3 * g + t], src = qbase | (h / 3), ht = h % 3;
-    const float f0 = shfl(O.actf[0], src), f1 = shfl(O.actf[1], src), f2 = shfl(O.actf[2], src);
-    afA[t] = ht == 0 ? f0 : (ht == 1 ? f1 : f2);
-  }
-#pragma unroll
-  for (int t = 0; t < 3; t++) {
-    const float q = X.ql[t], dq = q - L.default_pose[t], af = O.actf[t];
-    vals[0] += fabsf(dq);
-    vals[1] += dq * dq * ((t == 0) ? 1.0f : 0.1f);
-    const float a = q - L.soft_lo[t], b = q - L.soft_hi[t];
-    vals[2] += -(a < 0.f ? a : 0.f) + (b > 0.f ? b : 0.f);
-    vals[3] += af * af; vals[4] += fabsf(af);
-    vals[5] += (actA[t] - last_act[t]) * (actA[t] - last_act[t]);
-    vals[6] += fabsf(X.vl[t]) * fabsf(afA[t]);
-  }
-  {
-    const float* v = Z.fvel; const float* pf = Z.fpos;
-    const float vxy2 = v[0] * v[0] + v[1] * v[1];
-    vals[7] = vxy2 * (float)contact;
-    vals[8] = (GC.variant ? fabsf(Z.fworld[2] - (hmax - GC.base_feet_distance + GC.swing_height))   // world-frame foot height, joystick.py:569-572
-                          : fabsf(pf[2] - (hmax + GC.swing_height))) * sqrtf(sqrtf(vxy2));
-    const float rz = gait_get_z(phase, hmax + GC.swing_height, GC.base_feet_distance);
-    vals[9] = (pf[2] - rz) * (pf[2] - rz);
-    const int swing_mask = (phase / (2.f * PGTT_PI)) >= 0.5f;
-    vals[10] = (pf[2] - GC.swing_height) * (pf[2] - GC.swing_height) * (float)swing_mask;
-    vals[11] = (air - (GC.variant ? 0.5f : 0.1f)) * (float)first_contact;   // joystick.py:591 vs joystick_pgtt.py:597
-    vals[12] = (float)(swing_mask && contact);
-    vals[13] = pf[0] * pf[0] + pf[1] * pf[1];
-    const float er = swing_peak / GC.swing_height - 1.f;
-    vals[14] = er * er * (float)first_contact;
-  }
-  float sums[15];
-#pragma unroll
-  for (int k = 0; k < 15; k++) sums[k] = qsum(vals[k]);
-  const float footz = qmin(Z.fworld[2]);
-  float reward, rw[NREW];
-  {
-    const float le = (cmd0 - Z.llin[0]) * (cmd0 - Z.llin[0]) + (cmd1 - Z.llin[1]) * (cmd1 - Z.llin[1]);
-    rw[0] = expf(-le / GC.tracking_sigma);
-    rw[1] = expf(-((cmd2 - Z.gyro[2]) * (cmd2 - Z.gyro[2])) / GC.tracking_sigma);
-    rw[2] = Z.glin[2] * Z.glin[2];
-    rw[3] = Z.gang[0] * Z.gang[0] + Z.gang[1] * Z.gang[1];
-    rw[4] = Z.up[0] * Z.up[0] + Z.up[1] * Z.up[1];
-    rw[5] = sums[2];
-    rw[6] = sums[1];
-    rw[7] = (float)done;
-    rw[8] = sums[0] * (float)(cmd_norm < 0.01f);
-    rw[9] = sqrtf(sums[3]) + sums[4];
-    rw[10] = sums[5];
-    rw[11] = sums[6];
-    rw[12] = sums[8];
-    rw[13] = sums[14] * (float)(cmd_norm > 0.01f);
-    rw[14] = sums[7] * (float)(cmd_norm > 0.01f);
-    rw[15] = sums[11] * (float)(cmd_norm > 0.01f);
-    rw[16] = expf(-sums[9] / GC.phase_sigma);
-    rw[17] = sums[10];
-    const float bh = X.qb[2] - footz - 0.27f;
-    rw[18] = bh * bh;
-    rw[19] = -sums[12];
-    rw[20] = sums[13];
-#pragma unroll
-    for (int k = 0; k < NREW; k++) rw[k] *= GC.reward_scale[k];
-    // sum in the dict order of _get_reward
-    const float total = ((((((((((((((((((((rw[0] + rw[1]) + rw[2]) + rw[3]) + rw[4]) + rw[8]) + rw[7]) + rw[6]) + rw[9]) + rw[10]) + rw[11]) +
-                        rw[14]) + rw[12]) + rw[16]) + rw[18]) + rw[17]) + rw[15]) + rw[5]) + rw[19]) + rw[20]) + rw[13]);
-    reward = fminf(fmaxf(total * dt, 0.f), 10000.f);
-  }
-  // info bookkeeping (joystick_pgtt.py:205-224)
-  int steps_until = B.steps_until[env] - 1;
-  const Key rng3 = rng;   // rng, key1, key2 = split(rng, 3): key1 / key2 are derived only when consumed
-  rng = rng_split(rng, 3, 0);
-  float new_cmd = command_g;
-  const bool resample = steps_until <= 0;
-  if (resample) {  // sample_command (joystick_pgtt.py:603-611)
-    const Key key1 = rng_split(rng3, 3, 1);
-    const Key y_rng = rng_split(key1, 4, 1), w_rng = rng_split(key1, 4, 2), z_rng = rng_split(key1, 4, 3);
-    const int i = g < 3 ? g : 0;
-    const float y = rng_uniform(y_rng, 3, i, GC.cmd_u_min[i], GC.cmd_u_max[i]);
-    const float z = (float)(rng_unit(z_rng, 3, i) < GC.cmd_b[i]);
-    const float ww = (float)(rng_unit(w_rng, 3, i) < 0.5f);
-    new_cmd = command_g - ww * (command_g - y * z);
-  }
-  if (done || steps_until <= 0) steps_until = (int)rintf(-log1pf(-rng_unit(rng_split(rng3, 3, 2), 1, 0)) * 5.0f / dt);
-  air *= (float)(!contact);
-  swing_peak *= (float)(!contact);
-  const float sp_mean = qsum(swing_peak) * 0.25f;
-  float done_out = (float)done;
   if (ok) {
+    if (g == 0) {
 #pragma unroll
-    for (int t = 0; t < 3; t++) { B.last_last_act[env * NU + 3 * g + t] = last_act[t]; B.last_act[env * NU + 3 * g + t] = actA[t]; }
-    B.phase[env * 4 + kf] = fmodf(phase + B.phase_dt[env], 2.f * PGTT_PI);
-    if (g < 3 && resample) B.command[env * 3 + g] = new_cmd;
-    B.feet_air_time[env * 4 + kf] = air;
-    B.last_contact[env * 4 + kf] = contact;
-    B.swing_peak[env * 4 + kf] = swing_peak;
-    B.contact[env * 4 + kf] = contact;
-    B.first_contact[env * 4 + kf] = first_contact;
+      for (int i = 0; i < 4; i++) if (i < nsub) B.solver_niter[env * 4 + i] = niter[i];
+    }
     q_store_data(B, env, g, X, S, Z, O, L, X.ctrl);
   }
-  syncwarp();   // the command / steps_until reads above precede the lane-0 writes below
-  if (ok && g == 0) {
-#pragma unroll
-    for (int k = 0; k < NREW; k++) B.metrics[env * NMETRIC + k] = rw[k];
-    B.metrics[env * NMETRIC + NREW] = sp_mean;
-    B.rng[env * 2] = rng.a; B.rng[env * 2 + 1] = rng.b;
-    B.step[env] = step + 1;
-    B.steps_until[env] = steps_until;
-    B.time[env] += GC.dt * (float)GC.n_substeps;
-  }
-  if (wrapped) {
-    // EpisodeWrapper.step
-    steps += 1.f;
-    const float done_inner = done_out;
-    const bool over = steps >= (float)GC.episode_length;
-    done_out = over ? 1.f : done_inner;
-    if (ok && g == 0) {
-      const float prev_done = B.episode_done[env];
-      float* em = B.episode_metrics + (size_t)env * 24;
-      B.truncation[env] = over ? 1.f - done_inner : 0.f;
-      B.steps[env] = steps;
-      em[0] = (em[0] + reward) * (1.f - prev_done);
-      em[1] = (em[1] + 1.f) * (1.f - prev_done);
-#pragma unroll
-      for (int k = 0; k < NREW; k++) em[2 + k] = (em[2 + k] + rw[k]) * (1.f - prev_done);
-      em[2 + NREW] = (em[2 + NREW] + sp_mean) * (1.f - prev_done);
-      B.episode_done[env] = done_out;
-    }
-    syncwarp();
-    // auto-reset: restore the cached first data / obs only (info is NOT reset)
-    if (ok && done_out != 0.f) {
-      for (int i = g; i < NQ; i += 4) B.qpos[env * NQ + i] = B.first_qpos[env * NQ + i];
-      for (int i = g; i < NV; i += 4) {
-        B.qvel[env * NV + i] = B.first_qvel[env * NV + i];
-        B.warm[env * NV + i] = B.first_warm[env * NV + i];
-        B.qacc[env * NV + i] = B.first_qacc[env * NV + i];
-      }
-      for (int i = g; i < NU; i += 4) { B.actuator_force[env * NU + i] = B.first_actuator_force[env * NU + i]; B.ctrl[env * NU + i] = GC.home_qpos[7 + i]; }
-      for (int i = g; i < NSENSOR; i += 4) B.sensordata[env * NSENSOR + i] = B.first_sensordata[env * NSENSOR + i];
-      for (int i = g; i < 15; i += 4) B.site_xpos[env * 15 + i] = B.first_site_xpos[env * 15 + i];
-      for (int i = g; i < 9; i += 4) B.site_xmat[env * 9 + i] = B.first_site_xmat[env * 9 + i];
-      for (int i = g; i < NCON; i += 4) B.contact_dist[env * NCON + i] = B.first_contact_dist[env * NCON + i];
-      for (int i = g; i < 2 * NCON; i += 4) B.contact_geom[env * NCON * 2 + i] = B.first_contact_geom[env * NCON * 2 + i];
-      for (int i = g; i < GC.nobs; i += 4) B.obs_state[(size_t)env * GC.nobs + i] = B.first_obs_state[(size_t)env * GC.nobs + i];
-      for (int i = g; i < GC.npriv; i += 4) B.obs_priv[(size_t)env * GC.npriv + i] = B.first_obs_priv[(size_t)env * GC.npriv + i];
-      if (g == 0) B.time[env] = 0.f;
-    }
-  }
-  if (ok && g == 0) { B.reward[env] = reward; B.done[env] = done_out; }
 }
 
 // mjx.forward with every intermediate dumped (parity probe; layout in pgtt_debug.h)
