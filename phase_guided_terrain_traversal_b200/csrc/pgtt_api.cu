@@ -19,15 +19,16 @@
 #include "pgtt_env.cuh"
 #include "pgtt_quad.cuh"
 
-#define MAX_WARPS_PER_BLOCK 16
+#define MAX_WARPS_PER_BLOCK 28   // x 72 registers x 7.3 KB workspace = one SM: 28 resident envs per SM
+#define ENV_CTAS_PER_SM 1
 #define WS_BYTES ((sizeof(WS) + 15) / 16 * 16)
 
 static thread_local std::string g_err;
 
-// Warps (= envs) per CTA, one CTA per SM: the warps of a CTA run the stages in lockstep so the
-// instruction stream is fetched once per CTA. Picks the count in [8, 16] that wastes the fewest
-// warp slots in the last wave over the SMs (4096 envs on 148 SMs -> 14 warps, 293 CTAs = 1.98 waves).
-// PGTT_WARPS_PER_BLOCK overrides (tuning / tests).
+// Warps (= envs) per CTA of the warp-per-env kernels. An SM holds 28 such warps (registers: 28 x 32 x 72; shared memory:
+// 28 x 7.3 KB), i.e. 4096 envs are ONE resident wave on 148 SMs; the warps of a CTA run the stages in lockstep so the
+// instruction stream is fetched once per CTA. Picks the count in [7, 14] that needs the fewest waves, then the fewest
+// idle warp slots. PGTT_WARPS_PER_BLOCK overrides (tuning / tests).
 static int pick_warps_per_block(int n_envs) {
   if (const char* s = getenv("PGTT_WARPS_PER_BLOCK")) {
     const int v = atoi(s);
@@ -40,9 +41,11 @@ static int pick_warps_per_block(int n_envs) {
 #endif
   int best = MAX_WARPS_PER_BLOCK;
   double best_cost = 1e30;
-  for (int w = MAX_WARPS_PER_BLOCK; w >= 8; w--) {
-    const long ctas = (n_envs + w - 1) / w, waves = (ctas + n_sm - 1) / n_sm;
-    const double cost = (double)waves * (1.0 + 0.02 * w);   // time ~ waves x (mildly growing per-wave time)
+  for (int w = MAX_WARPS_PER_BLOCK; w >= 7; w--) {
+    if ((MAX_WARPS_PER_BLOCK * ENV_CTAS_PER_SM) % w) continue;   // CTAs must tile the 28 warp slots of an SM
+    const long ctas = (n_envs + w - 1) / w, per_sm = (MAX_WARPS_PER_BLOCK * ENV_CTAS_PER_SM) / w, waves = (ctas + n_sm * per_sm - 1) / (n_sm * per_sm);
+    // fewest waves; then every SM busy (small batches want small CTAs); then the larger lockstep CTA
+    const double cost = (double)waves + (ctas * 10 < n_sm * 9 ? 0.5 : 0.0) + 0.001 * (MAX_WARPS_PER_BLOCK - w);
     if (cost < best_cost - 1e-12) { best_cost = cost; best = w; }
   }
   return best;
@@ -59,20 +62,23 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
   if (lane < NU) w.ctrl[lane] = B.ctrl[env * NU + lane];
   syncwarp();
   kinematics(w, lane);
-  collision(w, B, env, lane);
+  collision(w, B, env, lane, true);
   com_inertia_cdof(w, lane);
   crb_and_inertia(w, lane);
   velocity_rne(w, lane);
   smooth_forces(w, lane);
   Rows R;
   make_rows(w, R, lane);
-  arrow_factor(w, w.MB, w.MC, w.MA, lane);
-  arrow_solve(w, w.qs, w.qas, lane);
+  // the position-stage arrays share storage with the factorisation scratch: dump them before the factor is formed
   for (int i = lane; i < 39; i += 32) { o[DBG_XPOS + i] = (&w.xpos[0][0])[i]; o[DBG_XIPOS + i] = (&w.xipos[0][0])[i]; }
   for (int i = lane; i < 117; i += 32) o[DBG_XMAT + i] = (&w.xmat[0][0])[i];
   if (lane < 3) o[DBG_COM + lane] = w.com[lane];
   for (int i = lane; i < 130; i += 32) o[DBG_CINERT + i] = (&w.cinert[0][0])[i];
   for (int i = lane; i < 108; i += 32) o[DBG_CDOF + i] = (&w.cdof[0][0])[i];
+  if (lane < NV) o[DBG_BIAS + lane] = w.bias[lane];
+  syncwarp();
+  arrow_factor(w, w.MB, w.MC, w.MA, lane);
+  arrow_solve(w, w.qs, w.qas, lane);
   for (int e = lane; e < 324; e += 32) {
     const int i = e / 18, j = e % 18;
     float v = 0.f;
@@ -82,7 +88,7 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
     else if ((i - 6) / 3 == (j - 6) / 3) v = w.MA[((i - 6) / 3) * 9 + ((i - 6) % 3) * 3 + (j - 6) % 3];
     o[DBG_QM + e] = v;
   }
-  if (lane < NV) { o[DBG_BIAS + lane] = w.bias[lane]; o[DBG_QS + lane] = w.qs[lane]; o[DBG_QAS + lane] = w.qas[lane]; }
+  if (lane < NV) { o[DBG_QS + lane] = w.qs[lane]; o[DBG_QAS + lane] = w.qas[lane]; }
   if (lane < NCON) {
     float* c = o + DBG_CONTACT + 16 * lane;
     c[0] = w.c_dist[lane];
@@ -118,7 +124,10 @@ struct LaunchArgs {
   RecordSlot rec;
 };
 #define TASK_BYTES ((sizeof(TaskWS) + 15) / 16 * 16)
-#define TASK_WARPS 8   // warps (= envs) per CTA of the task kernel
+#define TASK_WARPS 7   // warps (= envs) per CTA of the task kernel; 4 CTAs x 7 warps x 72 registers per SM: 4096 envs are one wave of 586 CTAs
+#define SMEM_MAX (227 * 1024)
+// warps per CTA of the reset kernel: each carries a physics workspace and a task workspace
+#define RESET_WARPS ((int)(SMEM_MAX / (WS_BYTES + TASK_BYTES)) < MAX_WARPS_PER_BLOCK ? (int)(SMEM_MAX / (WS_BYTES + TASK_BYTES)) : MAX_WARPS_PER_BLOCK)
 
 DEV void dispatch(WS& w, TaskWS& t, const LaunchArgs& a, int env, int lane) {
   switch (a.op) {
@@ -140,7 +149,7 @@ DEV void dispatch(WS& w, TaskWS& t, const LaunchArgs& a, int env, int lane) {
 
 // generation-1 physics / reset kernels: one warp per env, workspace in shared memory (reset also carries a TaskWS per warp)
 template <int OP>
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 1) pgtt_env_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, ENV_CTAS_PER_SM) pgtt_env_kernel(LaunchArgs a) {
   extern __shared__ float4 smem4[];
   const int wpb = blockDim.x >> 5;
   const int warp = warp_index(), lane = threadIdx.x & 31;
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(32 * QWARPS_MAX) pgtt_quad_kernel(LaunchArgs a
 
 // task kernel (pgtt_task.cuh): one warp per env, TASK_WARPS envs per CTA
 template <int OP>
-__global__ void __launch_bounds__(32 * TASK_WARPS) pgtt_task_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(32 * TASK_WARPS, 4) pgtt_task_kernel(LaunchArgs a) {
   extern __shared__ float4 smem4[];
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const int env = blockIdx.x * TASK_WARPS + warp;
@@ -303,14 +312,14 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
     if (a.op == OP_TASK) pgtt_task_kernel<OP_TASK><<<blocks, 32 * TASK_WARPS, smem, st>>>(a);
     else pgtt_task_kernel<OP_SCAN><<<blocks, 32 * TASK_WARPS, smem, st>>>(a);
   } else if (e->quad && (a.op == OP_STEP || a.op == OP_DEBUG)) {
-    int qw = e->N >= 5000 ? QWARPS_MAX : 2;   // lockstep CTAs once there is more than one warp per scheduler
+    int qw = e->N >= 5000 ? QWARPS_MAX : 4;   // lockstep CTAs (shared instruction fetch)
     if (const char* s = getenv("PGTT_QUAD_WARPS")) { const int v = atoi(s); if (v >= 1 && v <= QWARPS_MAX) qw = v; }
     const int qwarps = (e->N + QENV - 1) / QENV, qblocks = (qwarps + qw - 1) / qw;
     const size_t qsmem = qw * ((sizeof(QShared) + 15) / 16 * 16);
     if (a.op == OP_STEP) pgtt_quad_kernel<OP_STEP><<<qblocks, 32 * qw, qsmem, st>>>(a);
     else pgtt_quad_kernel<OP_DEBUG><<<qblocks, 32 * qw, qsmem, st>>>(a);
   } else {
-    const int wpb = e->wpb;
+    const int wpb = a.op == OP_RESET ? (e->wpb < RESET_WARPS ? e->wpb : RESET_WARPS) : e->wpb;
     const int blocks = (e->N + wpb - 1) / wpb;
     const size_t smem = wpb * WS_BYTES;
     switch (a.op) {
@@ -387,7 +396,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
     CUDA_OK(cudaSetDevice(device));
     const size_t smem = MAX_WARPS_PER_BLOCK * WS_BYTES;
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + MAX_WARPS_PER_BLOCK * TASK_BYTES)));
+    CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RESET_WARPS * (WS_BYTES + TASK_BYTES))));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t qsmem = QWARPS_MAX * ((sizeof(QShared) + 15) / 16 * 16);
@@ -405,10 +414,17 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   }
   { static uint64_t next_serial = 1; e->serial = next_serial++; }
   e->device = device; e->N = num_envs; e->wpb = pick_warps_per_block(num_envs); e->terrain_dev = nullptr; e->n_terrains = 0; e->launches = 0; e->randomized = false;
-  // Kernel generation for step / debug-forward. Measured on B200 (profiles/r01c): the quad kernel needs ~0.7 ms per
-  // step up to 8192 envs (one or two latency-bound warps per scheduler) and the warp-per-env kernel 0.125 us per env,
-  // so the quad kernel wins from ~4.8k envs per GPU (1.15x at 6144, 1.45x at 8192). PGTT_KERNEL=warp|quad overrides.
-  e->quad = num_envs >= 5000;
+  // Physics-kernel generation for step / debug-forward. Measured on B200 (profiles/r02): the warp-per-env kernel holds 28
+  // envs per SM, so up to 148 x 28 = 4144 envs are ONE resident wave (0.37 ms); above that it needs a second wave (0.70 ms at
+  // 8192) while the quad kernel (8 envs per warp, latency-bound at ~0.46 - 0.63 ms up to 8192 envs) does not.
+  // PGTT_KERNEL=warp|quad overrides.
+  {
+    int n_sm = 148;
+#ifndef PGTT_HOST_EMU
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+#endif
+    e->quad = num_envs > n_sm * MAX_WARPS_PER_BLOCK * ENV_CTAS_PER_SM;
+  }
   if (const char* k = getenv("PGTT_KERNEL")) e->quad = strcmp(k, "quad") == 0;
   ModelConst& c = e->mc;
   memset(&c, 0, sizeof(c));
@@ -690,6 +706,14 @@ int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
 // graph replays of the rollout launch this handle's kernels without going through launch(): keep the counter honest
 void pgtt_internal_count_launches(pgtt_env* e, int64_t n) { if (e) e->launches += n; }
 
+// development / profiling aid (tools/kernel_times.py): one half of pgtt_step. part 0 = physics kernel, 1 = task kernel
+int pgtt_internal_step_part(pgtt_env* e, const float* action, int wrapped, int part, void* stream) {
+  if (int rc = check_ready(e, "pgtt_internal_step_part")) return rc;
+  LaunchArgs a; memset(&a, 0, sizeof(a));
+  a.op = part ? OP_TASK : OP_STEP; a.action = action; a.wrapped = wrapped;
+  if (int rc = launch(e, a, stream)) return rc;
+  return mark_launched(e, stream);
+}
 uint64_t pgtt_internal_serial(pgtt_env* e) { return e ? e->serial : 0; }
 int pgtt_internal_make_resident(pgtt_env* e, void* stream) { return e ? make_resident(e, stream) : PGTT_OK; }
 int pgtt_internal_mark_launched(pgtt_env* e, void* stream) { return e ? mark_launched(e, stream) : PGTT_OK; }

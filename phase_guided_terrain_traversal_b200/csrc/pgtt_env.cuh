@@ -16,7 +16,7 @@ DEV void store_data(WS& w, const EnvBuffers& B, int env, int lane) {
   if (lane < 12) {  // sites FL FR RL RR = leg order
     B.site_xpos[env * 15 + 3 + lane] = w.foot[lane / 3][lane % 3];
   }
-  if (lane < 9) B.site_xmat[env * 9 + lane] = w.xmat[0][lane];
+  if (lane < 9) B.site_xmat[env * 9 + lane] = w.xmat0[lane];
   if (lane < NCON) {
     const int c = lane;
     const int box = w.c_box[c];
@@ -41,7 +41,7 @@ DEV void env_physics(WS& w, const EnvBuffers& B, const float* action_all, int en
   }
   syncwarp();
   for (int s = 0; s < GC.n_substeps; s++) {
-    const int ni = forward(w, B, env, lane, s == GC.n_substeps - 1);
+    const int ni = forward(w, B, env, lane, s == GC.n_substeps - 1, s == 0);
     if (lane == 0) w.niter[s & 3] = ni;
     euler(w, lane);
   }
@@ -55,7 +55,7 @@ DEV void stage_task_from_ws(TaskWS& t, const WS& w, int lane) {
   if (lane < NV) t.qvel[lane] = w.qvel[lane];
   for (int i = lane; i < NSENSOR; i += 32) t.sens[i] = w.sens[i];
   if (lane < NU) { t.actf[lane] = w.actf[lane]; (&t.foot[0][0])[lane] = (&w.foot[0][0])[lane]; }
-  if (lane < 9) t.xmat0[lane] = w.xmat[0][lane];
+  if (lane < 9) t.xmat0[lane] = w.xmat0[lane];
   syncwarp();
 }
 
@@ -86,7 +86,7 @@ DEV void env_reset(WS& w, TaskWS& t, const EnvBuffers& B, const uint32_t* keys, 
   syncwarp();
   if (lane < NU) w.ctrl[lane] = w.qpos[7 + lane];
   syncwarp();
-  forward(w, B, env, lane, false);                       // mjx_env.init
+  forward(w, B, env, lane, false, true);                 // mjx_env.init
   float* hs = B.heightscan + (size_t)env * NRAY * 3;
   t_heightscan(t, boxes, w.qpos[0], w.qpos[1], w.qpos[2], 0.f, hs, lane);     // yaw = 0 (Q10)
   float zmax = -__int_as_float(0x7f800000);
@@ -94,7 +94,7 @@ DEV void env_reset(WS& w, TaskWS& t, const EnvBuffers& B, const uint32_t* keys, 
   zmax = warp_max(zmax);
   if (lane == 0) w.qpos[2] += zmax;
   syncwarp();
-  forward(w, B, env, lane, true);                        // mjx.forward at the lifted pose
+  forward(w, B, env, lane, true, true);                  // mjx.forward at the lifted pose
   const Key key1 = rng_split(rng, 3, 1), key2 = rng_split(rng, 3, 2);
   rng = rng_split(rng, 3, 0);
   const float tcmd = -log1pf(-rng_unit(key1, 1, 0)) * 5.0f;
@@ -139,7 +139,7 @@ DEV void env_reset(WS& w, TaskWS& t, const EnvBuffers& B, const uint32_t* keys, 
   if (lane < NU) B.first_actuator_force[env * NU + lane] = w.actf[lane];
   for (int i = lane; i < NSENSOR; i += 32) B.first_sensordata[env * NSENSOR + i] = w.sens[i];
   if (lane < 15) B.first_site_xpos[env * 15 + lane] = B.site_xpos[env * 15 + lane];
-  if (lane < 9) B.first_site_xmat[env * 9 + lane] = w.xmat[0][lane];
+  if (lane < 9) B.first_site_xmat[env * 9 + lane] = w.xmat0[lane];
   if (lane < NCON) B.first_contact_dist[env * NCON + lane] = B.contact_dist[env * NCON + lane];
   if (lane < 2 * NCON) B.first_contact_geom[env * NCON * 2 + lane] = B.contact_geom[env * NCON * 2 + lane];
   for (int i = lane; i < GC.nobs; i += 32) B.first_obs_state[(size_t)env * GC.nobs + i] = B.obs_state[(size_t)env * GC.nobs + i];
@@ -193,6 +193,6 @@ DEV void env_forward(WS& w, const EnvBuffers& B, int env, int lane) {
   load_state(w, B, env, lane);
   if (lane < NU) w.ctrl[lane] = B.ctrl[env * NU + lane];
   syncwarp();
-  forward(w, B, env, lane, true);
+  forward(w, B, env, lane, true, true);
   store_data(w, B, env, lane);
 }

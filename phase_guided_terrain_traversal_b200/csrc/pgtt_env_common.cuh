@@ -8,9 +8,13 @@
 // ----------------------------------------------------------------------------------------------
 struct Key { uint32_t a, b; };
 
+#ifdef PGTT_HOST_EMU
 DEV uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
-// noinline: ~170 instructions, called from ~25 sites of the obs / command / reset code
-DEV_NOINLINE Key threefry(Key k, uint32_t x0, uint32_t x1) {
+#else
+DEV uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }   // one SHF
+#endif
+// inlined: ~105 instructions per site, and independent draws of one lane interleave (the physics kernels do not draw)
+DEV Key threefry(Key k, uint32_t x0, uint32_t x1) {
   const uint32_t ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
   x0 += ks0; x1 += ks1;
 #define TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }

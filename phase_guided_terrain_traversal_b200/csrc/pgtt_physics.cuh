@@ -81,13 +81,7 @@ DEV void load_model(WS& w, const EnvBuffers& B, int env, int lane) {
   }
   float m = lane < NB ? B.m_mass[env * NB + lane] : 0.f;
   m = warp_sum(m);
-  if (lane == 0) { w.mtot_inv = 1.0f / m; w.floor_mu = B.m_floorfric[env]; }
-  if (GC.n_boxes > 0) {
-    const int t = B.terrain_index[env];
-    const float4* src = reinterpret_cast<const float4*>(B.terrain + (size_t)t * NBOX * BOXF);
-    float4* dst = reinterpret_cast<float4*>(&w.box[0][0]);
-    for (int i = lane; i < NBOX * BOXF / 4; i += 32) dst[i] = src[i];
-  }
+  if (lane == 0) { w.mtot_inv = 1.0f / m; w.floor_mu = B.m_floorfric[env]; w.near_ok = 0; }
   syncwarp();
 }
 
@@ -111,8 +105,8 @@ DEV void kinematics(WS& w, int lane) {
   R[6] = 2 * (qx * qz - qw * qy); R[7] = 2 * (qy * qz + qw * qx); R[8] = qw * qw - qx * qx - qy * qy + qz * qz;
   float p[3] = {w.qpos[0], w.qpos[1], w.qpos[2]};
   if (lane == 1) {
-    for (int i = 0; i < 3; i++) w.xpos[0][i] = p[i];
-    for (int i = 0; i < 9; i++) w.xmat[0][i] = R[i];
+    for (int i = 0; i < 3; i++) { w.xpos[0][i] = p[i]; w.xpos0[i] = p[i]; }
+    for (int i = 0; i < 9; i++) { w.xmat[0][i] = R[i]; w.xmat0[i] = R[i]; }
   }
   const int bh = 1 + 3 * g;
   float s, c;
@@ -380,11 +374,11 @@ DEV void velocity_rne(WS& w, int lane) {
     for (int i = 0; i < 6; i++) vb[i] += w.cdof[3 + k][i] * qd;
   }
   if (lane < 3) {
-    for (int i = 0; i < 6; i++) w.cdofd[lane][i] = 0.f;
-    w.cdofd[3 + lane][0] = 0.f; w.cdofd[3 + lane][1] = 0.f; w.cdofd[3 + lane][2] = 0.f;
-    for (int i = 0; i < 3; i++) w.cdofd[3 + lane][3 + i] = cdd[lane][i];
+    for (int i = 0; i < 6; i++) w.cdofd_base[lane][i] = 0.f;
+    w.cdofd_base[3 + lane][0] = 0.f; w.cdofd_base[3 + lane][1] = 0.f; w.cdofd_base[3 + lane][2] = 0.f;
+    for (int i = 0; i < 3; i++) w.cdofd_base[3 + lane][3 + i] = cdd[lane][i];
   }
-  if (lane == 3) for (int i = 0; i < 6; i++) w.cvel[0][i] = vb[i];
+  if (lane == 3) for (int i = 0; i < 6; i++) w.cvel_base[i] = vb[i];
   float fb[6], tmp[6], tmp2[6];
   inert_mul(fb, w.cinert[0], ab);
   inert_mul(tmp, w.cinert[0], vb);
@@ -403,8 +397,8 @@ DEV void velocity_rne(WS& w, int lane) {
     inert_mul(tmp, w.cinert[b], vp);
     cross_force(tmp2, vp, tmp);
     for (int i = 0; i < 6; i++) fl[t][i] += tmp2[i];
-    if (sub == t) {
-      for (int i = 0; i < 6; i++) { w.cvel[b][i] = vp[i]; w.cdofd[d][i] = cdot[i]; }
+    if (t == 2 && sub == 2) {   // the sensors read the calf velocity (foot linear velocity)
+      for (int i = 0; i < 6; i++) w.cvel_calf[g][i] = vp[i];
     }
   }
   for (int i = 0; i < 6; i++) { fl[1][i] += fl[2][i]; fl[0][i] += fl[1][i]; }
@@ -479,47 +473,135 @@ DEV float sphere_box_local(const float* bx, const float* p, float r, float* l, f
   return sqrtf(e0 * e0 + e1 * e1 + e2 * e2) - r;
 }
 
-DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
-  const float r = GC.foot_r;
+// squared centre distance, the broad-phase key (same order as mjx's |d| - (r + rbound): rbound is one constant).
+// Un-contracted so that the list pass and the full scan (and every kernel generation) get the same bits.
+DEV float sqdist3(float dx, float dy, float dz) { return mul_add_nofma(dz, dz, mul_add_nofma(dy, dy, dx * dx)); }
+
+// Per control step and foot: the boxes whose SURFACE can come within the foot radius (penetration tests) and the boxes
+// whose CENTRE can come within W_RCEN (broad-phase ranks) while the foot travels at most W_MARGIN from where the lists
+// were built. Both are conservative supersets, so scanning them gives bit-identical contact bookkeeping to scanning all
+// 100 boxes; travel beyond the margin, list overflow or a threshold above W_RCEN^2 falls back to the full scan.
+// The env's box table (3.2 KB, global memory) is read once per control step here; the per-substep passes only touch
+// the listed boxes (L1-resident).
+DEV void build_near(WS& w, const float4* bp, int lane) {
   const int nb = GC.n_boxes;
-  int ncand = 0;
-  // bounding-sphere distances of all 4 x 100 pairs; scratch aliases the inertia workspace, which is
-  // only filled after the collision stage (forward() runs collision right after kinematics)
-  float* bs = &w.cinert[0][0];
+  const float rp = (GC.foot_r + W_MARGIN) * 1.001f, rc = (W_RCEN + W_MARGIN) * 1.001f;
+  const float rp2 = rp * rp, rc2 = rc * rc;
   const unsigned lt = (1u << lane) - 1u;
-  const float r2 = r * r * 1.0001f;  // conservative pre-filter; the exact test runs only where it passes
   float ft[4][3];
 #pragma unroll
   for (int f = 0; f < 4; f++) { ft[f][0] = w.foot[f][0]; ft[f][1] = w.foot[f][1]; ft[f][2] = w.foot[f][2]; }
-#pragma unroll 1
+  int npen[4] = {0, 0, 0, 0}, ncen[4] = {0, 0, 0, 0};
+  float4 c0[4], c1[4];
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const int k = it * 32 + lane, kc = k < nb ? k : nb - 1;
+    c0[it] = ldg4(bp + 2 * kc); c1[it] = ldg4(bp + 2 * kc + 1);
+  }
+#pragma unroll
   for (int it = 0; it < 4; it++) {
     const int k = it * 32 + lane;
     const bool valid = k < nb;
-    const float* bx = w.box[valid ? k : 0];
-    const float4 b0 = *reinterpret_cast<const float4*>(bx), b1 = *reinterpret_cast<const float4*>(bx + 4);
-    unsigned maybe = 0u;
+    const float4 b0 = c0[it], b1 = c1[it];
 #pragma unroll
     for (int f = 0; f < 4; f++) {
       const float dx = b0.x - ft[f][0], dy = b0.y - ft[f][1], dz = b0.z - ft[f][2];
-      // broad-phase key: squared centre distance (same order as mjx's |d| - (r + rbound): rbound is one constant)
-      if (valid) bs[f * NBOX + k] = dx * dx + dy * dy + dz * dz;
       const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
       const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
-      if (valid && (e0 * e0 + e1 * e1 + e2 * e2 < r2)) maybe |= 1u << f;
+      const bool pen = valid && (e0 * e0 + e1 * e1 + e2 * e2 < rp2), cen = valid && (dx * dx + dy * dy + dz * dz < rc2);
+      const unsigned mp = wballot(pen), mc = wballot(cen);
+      if (pen) { const int i = npen[f] + popc(mp & lt); if (i < W_QPEN) w.pen_list[f][i] = k; }
+      if (cen) { const int i = ncen[f] + popc(mc & lt); if (i < W_QCEN) w.cen_list[f][i] = k; }
+      npen[f] += popc(mp); ncen[f] += popc(mc);
     }
-    if (any_lane(maybe != 0u)) {
+  }
+  bool over = false;
+#pragma unroll
+  for (int f = 0; f < 4; f++) over |= (npen[f] > W_QPEN) || (ncen[f] > W_QCEN);
+  if (lane < 4) {
+#pragma unroll
+    for (int f = 0; f < 4; f++) if (lane == f) { w.near_npen[f] = npen[f]; w.near_ncen[f] = ncen[f]; }
+    w.near_f0[lane][0] = w.foot[lane][0]; w.near_f0[lane][1] = w.foot[lane][1]; w.near_f0[lane][2] = w.foot[lane][2];
+  }
+  if (lane == 0) w.near_ok = over ? 0 : 1;
+  syncwarp();
+}
+
+DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane, bool build) {
+  const float r = GC.foot_r;
+  const int nb = GC.n_boxes;
+  const float4* bp = reinterpret_cast<const float4*>(B.terrain + (size_t)B.terrain_index[env] * NBOX * BOXF);
+  if (build) build_near(w, bp, lane);
+  // lists usable: built without overflow and no foot further than the margin from where they were built (warp-uniform)
+  bool lists_ok = w.near_ok != 0;
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    const float tx = w.foot[f][0] - w.near_f0[f][0], ty = w.foot[f][1] - w.near_f0[f][1], tz = w.foot[f][2] - w.near_f0[f][2];
+    lists_ok = lists_ok && (tx * tx + ty * ty + tz * tz <= W_MARGIN * W_MARGIN);
+  }
+  const bool full = GC.quad_fullscan || !all_lanes(lists_ok);
+  int ncand = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  const float r2 = r * r * 1.0001f;  // conservative pre-filter; the exact test runs only where it passes
+  if (!full) {
+    // narrow phase over the penetration lists: 8 lanes per foot, one listed box per lane
+    const int f = lane >> 3, j = lane & 7;
+    const bool have = j < w.near_npen[f];
+    const int k = have ? w.pen_list[f][j] : 0;
+    const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
+    const float fx = w.foot[f][0], fy = w.foot[f][1], fz = w.foot[f][2];
+    const float dx = b0.x - fx, dy = b0.y - fy, dz = b0.z - fz;
+    const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
+    const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
+    const bool maybe = have && (e0 * e0 + e1 * e1 + e2 * e2 < r2);
+    if (any_lane(maybe)) {
+      const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float l[3], pt[3];
+      const float dist = maybe ? sphere_box_local(bx, w.foot[f], r, l, pt) : 1.f;
+      const bool hit = maybe && dist < 0.f;
+      const unsigned m = wballot(hit);
+      if (hit) {
+        const int idx = popc(m & lt);
+        if (idx < MAXCAND) { w.cand.pair[idx] = f * NBOX + k; w.cand.dist[idx] = dist; w.cand.cd2[idx] = sqdist3(dx, dy, dz); }
+      }
+      ncand = popc(m);
+    }
+  } else {
+    float ft[4][3];
+#pragma unroll
+    for (int f = 0; f < 4; f++) { ft[f][0] = w.foot[f][0]; ft[f][1] = w.foot[f][1]; ft[f][2] = w.foot[f][2]; }
 #pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+      const int k = it * 32 + lane;
+      const bool valid = k < nb;
+      const int kc = valid ? k : 0;
+      const float4 b0 = ldg4(bp + 2 * kc), b1 = ldg4(bp + 2 * kc + 1);
+      unsigned maybe = 0u;
+#pragma unroll
       for (int f = 0; f < 4; f++) {
-        const bool mb = (maybe >> f) & 1u;
-        float l[3], pt[3];
-        const float dist = mb ? sphere_box_local(bx, w.foot[f], r, l, pt) : 1.f;
-        const bool hit = mb && dist < 0.f;
-        const unsigned m = wballot(hit);
-        if (hit) {
-          const int idx = ncand + popc(m & lt);
-          if (idx < MAXCAND) { w.cand_pair[idx] = f * NBOX + k; w.cand_dist[idx] = dist; w.cand_cd2[idx] = bs[f * NBOX + k]; }
+        const float dx = b0.x - ft[f][0], dy = b0.y - ft[f][1], dz = b0.z - ft[f][2];
+        const float e0 = fmaxf(fabsf(b1.z * dx + b1.w * dy) - b0.w, 0.f), e1 = fmaxf(fabsf(b1.z * dy - b1.w * dx) - b1.x, 0.f);
+        const float e2 = fmaxf(fabsf(dz) - b1.y, 0.f);
+        if (valid && (e0 * e0 + e1 * e1 + e2 * e2 < r2)) maybe |= 1u << f;
+      }
+      if (any_lane(maybe != 0u)) {
+        const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll 1
+        for (int f = 0; f < 4; f++) {
+          const bool mb = (maybe >> f) & 1u;
+          float l[3], pt[3];
+          const float dist = mb ? sphere_box_local(bx, w.foot[f], r, l, pt) : 1.f;
+          const bool hit = mb && dist < 0.f;
+          const unsigned m = wballot(hit);
+          if (hit) {
+            const int idx = ncand + popc(m & lt);
+            if (idx < MAXCAND) {
+              w.cand.pair[idx] = f * NBOX + k; w.cand.dist[idx] = dist;
+              w.cand.cd2[idx] = sqdist3(b0.x - ft[f][0], b0.y - ft[f][1], b0.z - ft[f][2]);
+            }
+          }
+          ncand += popc(m);
         }
-        ncand += popc(m);
       }
     }
   }
@@ -534,16 +616,33 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
 #pragma unroll 1
     for (int c = 0; c < ncand; c++) {
       int cnt = 0;
-      const float t = w.cand_cd2[c];
-      const int pi = w.cand_pair[c];
+      const float t = w.cand.cd2[c];
+      const int pi = w.cand.pair[c];
+      if (!full && t < W_RCEN * W_RCEN) {
+        // every pair that can precede this one has its centre within W_RCEN of its foot: it is in that foot's centre list
+        const int f = lane >> 3;
+        const float fx = w.foot[f][0], fy = w.foot[f][1], fz = w.foot[f][2];
+        const int n = w.near_ncen[f];
 #pragma unroll 1
-      for (int f = 0; f < 4; f++)
-#pragma unroll 1
-        for (int k = lane; k < nb; k += 32) {
-          const float v = bs[f * NBOX + k];
+        for (int j = lane & 7; j < n; j += 8) {
+          const int k = w.cen_list[f][j];
+          const float4 b0 = ldg4(bp + 2 * k);
+          const float v = sqdist3(b0.x - fx, b0.y - fy, b0.z - fz);
           const int id = f * NBOX + k;
           cnt += (v < t) || (v == t && id < pi);
         }
+      } else {
+#pragma unroll 1
+        for (int k = lane; k < nb; k += 32) {
+          const float4 b0 = ldg4(bp + 2 * k);
+#pragma unroll
+          for (int f = 0; f < 4; f++) {
+            const float v = sqdist3(b0.x - w.foot[f][0], b0.y - w.foot[f][1], b0.z - w.foot[f][2]);
+            const int id = f * NBOX + k;
+            cnt += (v < t) || (v == t && id < pi);
+          }
+        }
+      }
       cnt = warp_sum_i(cnt);
       if (lane == c) mycnt = cnt;
     }
@@ -551,8 +650,8 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
   // keep the max_contact_points deepest of the surviving pairs (ties -> broad-phase order, then slot order)
   const float inf = __int_as_float(0x7f800000);
   const bool mine = lane < ncand && !(cull && mycnt >= GC.max_geom_pairs);
-  float myd = mine ? w.cand_dist[lane] : inf;
-  const int mypair = w.cand_pair[lane < ncand ? lane : 0];
+  float myd = mine ? w.cand.dist[lane] : inf;
+  const int mypair = w.cand.pair[lane < ncand ? lane : 0];
   const int maxc = GC.max_contact_points < 4 ? GC.max_contact_points : 4;
 #pragma unroll 1
   for (int s = 0; s < maxc; s++) {
@@ -563,7 +662,8 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
     const unsigned win = wballot(tie && mycnt == cm);
     if (lane == ffs_(win) - 1) {
       const int c = 4 + s, f = mypair / NBOX, k = mypair % NBOX;
-      const float* bx = w.box[k];
+      const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
+      const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float l[3], pt[3];
       const float dist = sphere_box_local(bx, w.foot[f], r, l, pt);
       float nl[3] = {pt[0] - l[0], pt[1] - l[1], pt[2] - l[2]};
@@ -583,7 +683,7 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane) {
   }
 }
 
-DEV void collision(WS& w, const EnvBuffers& B, int env, int lane) {
+DEV void collision(WS& w, const EnvBuffers& B, int env, int lane, bool build_lists) {
   const float r = GC.foot_r;
   if (lane < 4) {
     const int c = lane;
@@ -597,7 +697,7 @@ DEV void collision(WS& w, const EnvBuffers& B, int env, int lane) {
     w.c_dist[lane] = 1.f; w.c_leg[lane] = 0; w.c_box[lane] = -2;  // empty slot
   }
   const int nb = GC.n_boxes;
-  if (nb > 0) collide_boxes(w, B, env, lane);
+  if (nb > 0) collide_boxes(w, B, env, lane, build_lists);
   stage_sync(w, ST_COLLIDE);
 }
 
@@ -968,23 +1068,23 @@ DEV int solve(WS& w, Rows& R, int lane) {
 // sensors (App. A9) - evaluated from the forward pass of the substep, i.e. pre-integration (Q2)
 // ----------------------------------------------------------------------------------------------
 DEV void sensors(WS& w, int lane) {
-  const float* R = w.xmat[0];
+  const float* R = w.xmat0;
   if (lane < 4) {
     // sensor slot k = FR FL RR RL  ->  leg (qpos order FL FR RL RR)
     const int k = lane, g = k ^ 1;
     float imu[3];
-    for (int i = 0; i < 3; i++) imu[i] = w.xpos[0][i] + R[3 * i] * GC.imu_pos[0] + R[3 * i + 1] * GC.imu_pos[1] + R[3 * i + 2] * GC.imu_pos[2];
+    for (int i = 0; i < 3; i++) imu[i] = w.xpos0[i] + R[3 * i] * GC.imu_pos[0] + R[3 * i + 1] * GC.imu_pos[1] + R[3 * i + 2] * GC.imu_pos[2];
     const float rel[3] = {w.foot[g][0] - imu[0], w.foot[g][1] - imu[1], w.foot[g][2] - imu[2]};
     for (int i = 0; i < 3; i++) w.sens[25 + 3 * k + i] = R[i] * rel[0] + R[3 + i] * rel[1] + R[6 + i] * rel[2];
-    const float* cv = w.cvel[3 + 3 * g];
+    const float* cv = w.cvel_calf[g];
     const float off[3] = {w.foot[g][0] - w.com[0], w.foot[g][1] - w.com[1], w.foot[g][2] - w.com[2]};
     float c[3];
     cross3(c, cv, off);
     for (int i = 0; i < 3; i++) w.sens[37 + 3 * k + i] = cv[3 + i] + c[i];
   } else if (lane == 4) {
     float imu[3];
-    for (int i = 0; i < 3; i++) imu[i] = w.xpos[0][i] + R[3 * i] * GC.imu_pos[0] + R[3 * i + 1] * GC.imu_pos[1] + R[3 * i + 2] * GC.imu_pos[2];
-    const float* cv = w.cvel[0];
+    for (int i = 0; i < 3; i++) imu[i] = w.xpos0[i] + R[3 * i] * GC.imu_pos[0] + R[3 * i + 1] * GC.imu_pos[1] + R[3 * i + 2] * GC.imu_pos[2];
+    const float* cv = w.cvel_base;
     const float off[3] = {imu[0] - w.com[0], imu[1] - w.com[1], imu[2] - w.com[2]};
     float c[3], lin[3];
     cross3(c, cv, off);
@@ -1005,7 +1105,7 @@ DEV void sensors(WS& w, int lane) {
     float cacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, -GC.gravity_z};
     for (int k = 0; k < 6; k++) {
       const float qd = w.qvel[k], qa = w.qacc[k];
-      for (int i = 0; i < 6; i++) cacc[i] += w.cdofd[k][i] * qd + w.cdof[k][i] * qa;
+      for (int i = 0; i < 6; i++) cacc[i] += w.cdofd_base[k][i] * qd + w.cdof[k][i] * qa;
     }
     float c1[3], corr[3];
     cross3(c1, cacc, off);
@@ -1021,9 +1121,9 @@ DEV void sensors(WS& w, int lane) {
 // ----------------------------------------------------------------------------------------------
 // mjx.forward and the Euler update
 // ----------------------------------------------------------------------------------------------
-DEV int forward(WS& w, const EnvBuffers& B, int env, int lane, bool with_sensors) {
+DEV int forward(WS& w, const EnvBuffers& B, int env, int lane, bool with_sensors, bool build_lists) {
   kinematics(w, lane);
-  collision(w, B, env, lane);   // before the inertia stages: its scratch aliases w.cinert
+  collision(w, B, env, lane, build_lists);   // before the inertia stages: its scratch aliases w.crb
   com_inertia_cdof(w, lane);
   crb_and_inertia(w, lane);
   velocity_rne(w, lane);

@@ -194,30 +194,49 @@ DEV void t_stage_data(TaskWS& t, const EnvBuffers& B, int env, int lane) {
 // ----------------------------------------------------------------------------------------------
 DEV void task_step(TaskWS& t, const EnvBuffers& B, const float* action_all, int env, int lane, int wrapped, const RecordSlot& rec) {
   const float dt = GC.ctrl_dt;
+  // every independent global load of the step is issued up front (one DRAM round trip instead of a dozen dependent ones)
+  const float* boxes = t_env_boxes(B, env);
+  const float steps_in = wrapped ? B.steps[env] : 0.f, done_in = wrapped ? B.done[env] : 0.f;
+  const float action = lane < NU ? action_all[(size_t)env * NU + lane] : 0.f;
+  const int c_geom = lane < NCON ? B.contact_geom[env * NCON * 2 + 2 * lane + (lane < 4 ? 1 : 0)] : -1;
+  const float c_dist = lane < NCON ? B.contact_dist[env * NCON + lane] : 0.f;
+  const int last_contact = lane < 4 ? B.last_contact[env * 4 + lane] : 0;
+  float air = lane < 4 ? B.feet_air_time[env * 4 + lane] : 0.f;
+  const float swing_peak_in = lane < 4 ? B.swing_peak[env * 4 + lane] : 0.f;
+  Key rng; rng.a = B.rng[env * 2]; rng.b = B.rng[env * 2 + 1];
+  const float phase = lane < 4 ? B.phase[env * 4 + lane] : 0.f;
+  const float last_act = lane < NU ? B.last_act[env * NU + lane] : 0.f;
+  const float command = lane < 3 ? B.command[env * 3 + lane] : 0.f;
+  const int step = B.step[env];
+  const float gait_freq = B.gait_freq[env], phase_dt = B.phase_dt[env];
+  const int steps_until_in = B.steps_until[env];
+  const float prev_ep_done = wrapped ? B.episode_done[env] : 0.f;
+  const float em_in = (wrapped && lane < 24) ? B.episode_metrics[(size_t)env * 24 + lane] : 0.f;
+  const float time_in = B.time[env];
   t_stage_data(t, B, env, lane);
   // BraxAutoResetWrapper.step: steps <- 0 where the previous step ended an episode; done cleared
-  float steps = 0.f;
-  if (wrapped) { steps = B.steps[env]; if (B.done[env] != 0.f) steps = 0.f; }
-  float action = 0.f;
-  if (lane < NU) action = action_all[(size_t)env * NU + lane];
+  float steps = (done_in != 0.f) ? 0.f : steps_in;
   // compute_contact (base.py:153-171): any listed contact of the foot with dist < 0. Flag order FR FL RR RL, contact
-  // list = 4 foot/plane slots (floor geom, foot geom) + 4 foot/box slots (foot geom, box geom); empty slots hold -1
-  int contact = 0, first_contact = 0, last_contact = 0;
-  float air = 0.f, swing_peak = 0.f;
-  if (lane < 4) {
-    const int fg = GC.foot_geom[lane ^ 1];
-    for (int c = 0; c < NCON; c++) {
-      const int geom = B.contact_geom[env * NCON * 2 + 2 * c + (c < 4 ? 1 : 0)];
-      if (geom == fg && B.contact_dist[env * NCON + c] < 0.f) contact = 1;
+  // list = 4 foot/plane slots (floor geom, foot geom) + 4 foot/box slots (foot geom, box geom); empty slots hold -1.
+  // Lane c < 8 holds contact c: one ballot per foot.
+  int contact = 0, first_contact = 0;
+  float swing_peak = 0.f;
+  {
+    const bool hit = lane < NCON && c_dist < 0.f;
+    unsigned m[4];
+#pragma unroll
+    for (int f = 0; f < 4; f++) m[f] = wballot(hit && c_geom == GC.foot_geom[f]);
+    if (lane < 4) {
+      const int g = lane ^ 1;
+#pragma unroll
+      for (int f = 0; f < 4; f++) if (f == g) contact = m[f] != 0u;
+      first_contact = (air > 0.f) && (contact | last_contact);
+      air += dt;
+      swing_peak = fmaxf(swing_peak_in, t.sens[25 + 3 * lane + 2]);
     }
-    last_contact = B.last_contact[env * 4 + lane];
-    air = B.feet_air_time[env * 4 + lane];
-    first_contact = (air > 0.f) && (contact | last_contact);
-    air += dt;
-    swing_peak = fmaxf(B.swing_peak[env * 4 + lane], t.sens[25 + 3 * lane + 2]);
   }
   // height scan at the post-step pose, quadrant statistics (joystick_pgtt.py:167-190, Q8)
-  t_heightscan(t, t_env_boxes(B, env), t.qpos[0], t.qpos[1], t.qpos[2], quat_to_yaw(t.qpos + 3), B.heightscan + (size_t)env * NRAY * 3, lane);
+  t_heightscan(t, boxes, t.qpos[0], t.qpos[1], t.qpos[2], quat_to_yaw(t.qpos + 3), B.heightscan + (size_t)env * NRAY * 3, lane);
   float hmax = 0.f;
   {
     // quadrant q of this lane group: rows/cols per joystick_pgtt.py:171-174 (n = 6)
@@ -237,17 +256,11 @@ DEV void task_step(TaskWS& t, const EnvBuffers& B, const float* action_all, int 
     if (lane < 4) { B.H_max[env * 4 + lane] = hmax; B.H_min[env * 4 + lane] = hmin; }
   }
   // observation (uses info BEFORE the bookkeeping below, except feet_air_time which is already += dt)
-  Key rng; rng.a = B.rng[env * 2]; rng.b = B.rng[env * 2 + 1];
-  float phase = 0.f, last_act = 0.f, command = 0.f;
-  if (lane < 4) phase = B.phase[env * 4 + lane];
-  if (lane < NU) last_act = B.last_act[env * NU + lane];
-  if (lane < 3) command = B.command[env * 3 + lane];
-  const int step = B.step[env];
   if (lane < 4) { t.phase[lane] = phase; t.air[lane] = air; t.last_contact[lane] = last_contact; }
   if (lane < NU) t.last_act[lane] = last_act;
   if (lane < 3) t.command[lane] = command;
   syncwarp();
-  t_write_obs(t, B, env, rng, B.gait_freq[env], lane);
+  t_write_obs(t, B, env, rng, gait_freq, lane);
   t_update_history(t, B, env, step, B.motor_targets + (size_t)env * NU, lane);
   // termination (joystick_pgtt.py:233-236) + a failure guard the reference does not have: a non-finite or
   // absurd generalised state ends the episode, so the auto-reset wrapper restores the env instead of carrying NaNs forever
@@ -331,8 +344,8 @@ DEV void task_step(TaskWS& t, const EnvBuffers& B, const float* action_all, int 
   }
   // info bookkeeping (joystick_pgtt.py:205-224)
   if (lane < NU) { B.last_last_act[env * NU + lane] = last_act; B.last_act[env * NU + lane] = action; }
-  if (lane < 4) B.phase[env * 4 + lane] = fmodf(phase + B.phase_dt[env], 2.f * PGTT_PI);
-  int steps_until = B.steps_until[env] - 1;
+  if (lane < 4) B.phase[env * 4 + lane] = fmodf(phase + phase_dt, 2.f * PGTT_PI);
+  int steps_until = steps_until_in - 1;
   const Key rng3 = rng;   // rng, key1, key2 = split(rng, 3): key1 / key2 are derived only when consumed
   rng = rng_split(rng, 3, 0);
   if (steps_until <= 0) {  // sample_command (joystick_pgtt.py:603-611)
@@ -368,7 +381,7 @@ DEV void task_step(TaskWS& t, const EnvBuffers& B, const float* action_all, int 
     B.rng[env * 2] = rng.a; B.rng[env * 2 + 1] = rng.b;
     B.step[env] = step + 1;
     B.steps_until[env] = steps_until;
-    B.time[env] += GC.dt * (float)GC.n_substeps;
+    B.time[env] = time_in + GC.dt * (float)GC.n_substeps;
   }
   float done_out = (float)done, trunc_out = 0.f;
   bool restored = false;
@@ -379,17 +392,17 @@ DEV void task_step(TaskWS& t, const EnvBuffers& B, const float* action_all, int 
     const bool over = steps >= (float)GC.episode_length;
     done_out = over ? 1.f : done_inner;
     trunc_out = over ? 1.f - done_inner : 0.f;
-    const float prev_done = B.episode_done[env];
-    float* em = B.episode_metrics + (size_t)env * 24;
+    // episode_metrics rows: [sum_reward, length, 22 metrics]; lane k holds row k, the step's increments come from lanes k - 2
+    {
+      const float inc_m = shfl(metric, lane >= 2 ? lane - 2 : 0);
+      const float inc = lane == 0 ? reward : (lane == 1 ? 1.f : inc_m);
+      if (lane < 24) B.episode_metrics[(size_t)env * 24 + lane] = (em_in + inc) * (1.f - prev_ep_done);
+    }
     if (lane == 0) {
       B.truncation[env] = trunc_out;
       B.steps[env] = steps;
-      em[0] = (em[0] + reward) * (1.f - prev_done);
-      em[1] = (em[1] + 1.f) * (1.f - prev_done);
+      B.episode_done[env] = done_out;
     }
-    if (lane < NMETRIC) em[2 + lane] = (em[2 + lane] + metric) * (1.f - prev_done);
-    syncwarp();
-    if (lane == 0) B.episode_done[env] = done_out;
     // auto-reset: restore the cached first data / obs only (info is NOT reset)
     if (done_out != 0.f) {
       restored = true;

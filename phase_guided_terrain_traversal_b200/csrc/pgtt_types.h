@@ -76,39 +76,60 @@ struct EnvBuffers {
   int n_terrains;
 };
 
-// Per-warp shared-memory workspace (one env per warp).
+// near-box lists of the warp-per-env collision stage (per foot; overflow falls back to the full scan)
+#define W_QPEN 8           // boxes whose surface can reach the foot within one control step
+#define W_QCEN 16          // boxes whose centre can come within W_RCEN of the foot
+#define W_MARGIN 0.12f     // foot travel covered by the lists (checked every substep)
+#define W_RCEN 0.9f        // broad-phase thresholds below W_RCEN^2 are ranked from the centre lists
+
+// Per-warp shared-memory workspace of the warp-per-env physics kernel (one env per warp). Kept under 8 KB so that 28
+// warps (two CTAs of 14) fit one SM: 4096 envs are ONE resident wave on 148 SMs. Arrays that are only alive in one
+// phase of mjx.forward share storage: position-stage scratch (link frames, composite inertias, RNE forces, collision
+// candidates) with the factorisation / Hessian scratch of the solver.
 struct WS {
-  float box[NBOX][BOXF];
   // state
   float qpos[20], qvel[NV], qacc[NV], warm[NV], ctrl[NU];
   // per-env model
   float mass[NB], ipos0[3], armature[12], damping[12], gain[12], bias1[12], qpos0[12];
   float mtot_inv, floor_mu;
-  // kinematics (index 0 = base, 1+3g+t = leg g link t)
-  float xpos[NB][3], xmat[NB][9], xipos[NB][3], com[3];
-  float cinert[NB][10], crb[NB][10], cdof[NV][6], cdofd[NV][6], cvel[NB][6], F[NV][6];
+  // kinematics that outlive the position stage
+  float xpos0[3], xmat0[9], com[3];                 // base frame (= imu site orientation), subtree COM
+  float cinert[NB][10], cdof[NV][6];
+  float cdofd_base[6][6], cvel_base[6], cvel_calf[NLEG][6];   // what the sensors read of cdof_dot / cvel
   float foot[NLEG][3];
-  // arrow matrices: base block [6][6], coupling [leg][6][3], leg blocks [leg][3][3]
+  // arrow inertia matrix: base block [6][6], coupling [leg][6][3], leg blocks [leg][3][3]
   float MB[36], MC[72], MA[36];
-  float HB[36], HC[72], HA[36];
-  float fLA[NLEG][6];       // Cholesky of A_g: l00 l10 l11 l20 l21 l22 (diagonals stored as reciprocals)
-  float fY[NLEG][6][3];     // C_g A_g^-1
-  float fS[36];             // Schur complement of the base block
-  float fL[24];             // its Cholesky factor, row-packed lower, diagonals as reciprocals (21 used)
-  float tb[6];
   // vectors
-  float bias[NV], qs[NV], qas[NV], Ma[NV], grad[NV], search[NV], mv[NV], qfc[NV];
+  float qs[NV], qas[NV], Ma[NV], grad[NV], search[NV], mv[NV], qfc[NV];
   float actf[NU];
   // contacts: slots 0..3 = foot g vs floor, 4..7 = selected foot-box contacts
   int c_leg[NCON], c_box[NCON];
   float c_dist[NCON], c_pos[NCON][3], c_frame[NCON][9], c_mu[NCON];
-  float Jc[NCON][3][9], Ac[NCON][6], fc[NCON][3], limD[12];
+  float Jc[NCON][3][9], Ac[NCON][5], fc[NCON][3], limD[12];
   int nact, actlist[NCON];
-  int cand_n, cand_pair[MAXCAND], cand_cnt[MAXCAND];
-  float cand_dist[MAXCAND], cand_cd2[MAXCAND];
-  int boxlist[NBOX];
-  float scan[NRAY];
+  // near-box lists, built at the first substep of a control step
+  int pen_list[NLEG][W_QPEN], cen_list[NLEG][W_QCEN];
+  float near_f0[NLEG][3];
+  int near_npen[NLEG], near_ncen[NLEG], near_ok;
   float sens[NSENSOR];
   int niter[4];
   int bar_threads;  // threads of this CTA that take part in stage barriers (32 x live warps)
+  union {
+    struct {        // position / velocity stage (index 0 = base, 1+3g+t = leg g link t)
+      float xpos[NB][3], xmat[NB][9], xipos[NB][3];
+      union {
+        float crb[NB][10];
+        struct { int pair[MAXCAND]; float dist[MAXCAND], cd2[MAXCAND]; } cand;   // collision runs before the inertia stages
+      };
+      float F[NV][6], bias[NV];
+    };
+    struct {        // factorisation / solver stage
+      float HB[36], HC[72], HA[36];
+      float fLA[NLEG][6];       // Cholesky of A_g: l00 l10 l11 l20 l21 l22 (diagonals stored as reciprocals)
+      float fY[NLEG][6][3];     // C_g A_g^-1
+      float fS[36];             // Schur complement of the base block
+      float fL[24];             // its Cholesky factor, row-packed lower, diagonals as reciprocals (21 used)
+      float tb[6];
+    };
+  };
 };

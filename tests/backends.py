@@ -10,7 +10,7 @@ def make_env(kind, model, cfg, n, **kw):
     base, _, gen = kind.partition("-")
     if gen != "auto":   # "cuda-auto": the generation pgtt_create picks from the env count
         os.environ["PGTT_KERNEL"] = "quad" if gen.startswith("quad") else "warp"
-    os.environ["PGTT_QUAD_FULLSCAN"] = "1" if gen == "quadfull" else "0"
+    os.environ["PGTT_QUAD_FULLSCAN"] = "1" if gen in ("quadfull", "warpfull") else "0"   # full box scans instead of the near lists
     try:
         if base == "emu":
             import emu_backend
@@ -22,5 +22,5 @@ def make_env(kind, model, cfg, n, **kw):
         os.environ.pop("PGTT_QUAD_FULLSCAN", None)
 
 
-BACKENDS = [pytest.param("emu", id="emu"), pytest.param("emu-quad", id="emu-quad"), pytest.param("emu-quadfull", id="emu-quadfull"),
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("emu-warpfull", id="emu-warpfull"), pytest.param("emu-quad", id="emu-quad"), pytest.param("emu-quadfull", id="emu-quadfull"),
             pytest.param("cuda", id="cuda", marks=pytest.mark.gpu), pytest.param("cuda-quad", id="cuda-quad", marks=pytest.mark.gpu)]

@@ -51,7 +51,7 @@ def test_b200_arm_line_carries_roofline_baseline_e2e_and_clocks():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert (KEYS - {"impl"}) | {"roofline", "gpu_launches", "clocks", "rollout"} <= set(d)
-    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["scaling"] == "weak" and d["gpu_launches"] == 20
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["scaling"] == "weak" and d["gpu_launches"] == 40   # physics + task kernel per step
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["kernel"].startswith("pgtt_")
     assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 12 * 4 and d["e2e"]["d2h_bytes_per_step"] == 4096 * 2 * 4 and 0 < d["e2e"]["value"] <= d["value"] * 1.05
