@@ -62,11 +62,11 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
   if (lane < NU) w.ctrl[lane] = B.ctrl[env * NU + lane];
   syncwarp();
   kinematics(w, lane);
-  collision(w, B, env, lane, true);
   com_inertia_cdof(w, lane);
   crb_and_inertia(w, lane);
   velocity_rne(w, lane);
   smooth_forces(w, lane);
+  collision(w, B, env, lane, true);
   Rows R;
   make_rows(w, R, lane);
   // the position-stage arrays share storage with the factorisation scratch: dump them before the factor is formed
@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, ENV_CTAS_PER_SM) pgt
   WS& w = *reinterpret_cast<WS*>(reinterpret_cast<char*>(smem4) + (size_t)warp * WS_BYTES);
   {
     const int live = a.B.N - blockIdx.x * wpb;
-    if (lane == 0) w.bar_threads = 32 * (live < wpb ? live : wpb);
+    if (lane == 0) { w.bar_threads = 32 * (live < wpb ? live : wpb); w.trace = nullptr; w.tix = 0; }
     syncwarp();
   }
-  if (OP == OP_STEP) env_physics(w, a.B, a.action, env, lane);
+  if (OP == OP_STEP) env_physics(w, a.B, a.action, env, lane, reinterpret_cast<long long*>(a.out));
   else if (OP == OP_RESET) {
     TaskWS& t = *reinterpret_cast<TaskWS*>(reinterpret_cast<char*>(smem4) + (size_t)wpb * WS_BYTES + (size_t)warp * TASK_BYTES);
     env_reset(w, t, a.B, a.keys, env, lane);
@@ -706,6 +706,16 @@ int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
 // graph replays of the rollout launch this handle's kernels without going through launch(): keep the counter honest
 void pgtt_internal_count_launches(pgtt_env* e, int64_t n) { if (e) e->launches += n; }
 
+// development aid (tools/stage_trace.py): one warp-per-env physics launch that records the SM clock of every warp after each
+// stage of every substep into trace[num_envs][40] (DEVICE, int64)
+int pgtt_internal_physics_trace(pgtt_env* e, const float* action, long long* trace, void* stream) {
+  if (int rc = check_ready(e, "pgtt_internal_physics_trace")) return rc;
+  if (e->quad) return fail(PGTT_ERR_STATE, "pgtt_internal_physics_trace: warp-per-env kernel only");
+  LaunchArgs a; memset(&a, 0, sizeof(a));
+  a.op = OP_STEP; a.action = action; a.out = reinterpret_cast<float*>(trace);
+  if (int rc = launch(e, a, stream)) return rc;
+  return mark_launched(e, stream);
+}
 // development / profiling aid (tools/kernel_times.py): one half of pgtt_step. part 0 = physics kernel, 1 = task kernel
 int pgtt_internal_step_part(pgtt_env* e, const float* action, int wrapped, int part, void* stream) {
   if (int rc = check_ready(e, "pgtt_internal_step_part")) return rc;

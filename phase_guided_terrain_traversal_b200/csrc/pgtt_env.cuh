@@ -32,7 +32,9 @@ DEV void store_data(WS& w, const EnvBuffers& B, int env, int lane) {
 // Leaves mjx.Data (qpos, qvel, warm start, qacc, ctrl, sensordata, actuator_force, site frames, contact list) in the
 // handle's buffers for the task kernel.
 // ----------------------------------------------------------------------------------------------
-DEV void env_physics(WS& w, const EnvBuffers& B, const float* action_all, int env, int lane) {
+DEV void env_physics(WS& w, const EnvBuffers& B, const float* action_all, int env, int lane, long long* trace = nullptr) {
+  if (lane == 0) { w.trace = trace ? trace + (size_t)env * 40 : nullptr; w.tix = 0; }
+  syncwarp();
   load_model(w, B, env, lane);
   load_state(w, B, env, lane);
   if (lane < NU) {
@@ -47,6 +49,7 @@ DEV void env_physics(WS& w, const EnvBuffers& B, const float* action_all, int en
   }
   if (lane < 4 && lane < GC.n_substeps) B.solver_niter[env * 4 + lane] = w.niter[lane];
   store_data(w, B, env, lane);
+  STAGE_TRACE(w, lane);   // 28: stored
 }
 
 // mjx.Data of the workspace -> the task layer's staging area (reset runs both layers in one kernel)

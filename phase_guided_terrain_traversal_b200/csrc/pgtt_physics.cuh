@@ -29,6 +29,13 @@ DEV void stage_sync(const WS& w, int id) {
   if ((GC.sync_mask >> id) & 1) cta_bar(w.bar_threads); else syncwarp();
 }
 
+// stage-timestamp trace (development aid): lane 0 of the warp appends the SM clock after a stage when tracing is on
+#ifdef PGTT_HOST_EMU
+#define STAGE_TRACE(w, lane) do { } while (0)
+#else
+#define STAGE_TRACE(w, lane) do { if ((w).trace && (lane) == 0) (w).trace[(w).tix++] = clock64(); } while (0)
+#endif
+
 #define PGTT_MINVAL 1e-15f
 #define PGTT_PI 3.14159265358979323846f
 
@@ -611,27 +618,41 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane, bool build
   // broad-phase rank of every penetrating pair among all 4*nb pairs (keep the max_geom_pairs nearest
   // centres); lane c ends up owning candidate c
   const bool cull = (GC.max_geom_pairs > -1) && (4 * nb > GC.max_geom_pairs);
+  const float inf = __int_as_float(0x7f800000);
   int mycnt = 0;
   if (cull) {
+    const float myt = lane < ncand ? w.cand.cd2[lane] : 0.f;
+    // every pair that can precede a candidate with threshold < W_RCEN^2 has its centre within W_RCEN of its foot: it is in
+    // that foot's centre list. Each lane keys (at most) two listed pairs of its foot ONCE; a rank is then two ballots.
+    if (!full && all_lanes(myt < W_RCEN * W_RCEN)) {
+      const int f = lane >> 3, j = lane & 7, n = w.near_ncen[f];
+      const float fx = w.foot[f][0], fy = w.foot[f][1], fz = w.foot[f][2];
+      float v0 = inf, v1 = inf;
+      int id0 = 0x7fffffff, id1 = 0x7fffffff;
+      if (j < n) {
+        const int k = w.cen_list[f][j];
+        const float4 b0 = ldg4(bp + 2 * k);
+        v0 = sqdist3(b0.x - fx, b0.y - fy, b0.z - fz); id0 = f * NBOX + k;
+      }
+      if (j + 8 < n) {
+        const int k = w.cen_list[f][j + 8];
+        const float4 b0 = ldg4(bp + 2 * k);
+        v1 = sqdist3(b0.x - fx, b0.y - fy, b0.z - fz); id1 = f * NBOX + k;
+      }
+      static_assert(W_QCEN == 16, "two listed pairs per lane");
 #pragma unroll 1
-    for (int c = 0; c < ncand; c++) {
-      int cnt = 0;
-      const float t = w.cand.cd2[c];
-      const int pi = w.cand.pair[c];
-      if (!full && t < W_RCEN * W_RCEN) {
-        // every pair that can precede this one has its centre within W_RCEN of its foot: it is in that foot's centre list
-        const int f = lane >> 3;
-        const float fx = w.foot[f][0], fy = w.foot[f][1], fz = w.foot[f][2];
-        const int n = w.near_ncen[f];
+      for (int c = 0; c < ncand; c++) {
+        const float t = w.cand.cd2[c];
+        const int pi = w.cand.pair[c];
+        const int cnt = popc(wballot((v0 < t) || (v0 == t && id0 < pi))) + popc(wballot((v1 < t) || (v1 == t && id1 < pi)));
+        if (lane == c) mycnt = cnt;
+      }
+    } else {
 #pragma unroll 1
-        for (int j = lane & 7; j < n; j += 8) {
-          const int k = w.cen_list[f][j];
-          const float4 b0 = ldg4(bp + 2 * k);
-          const float v = sqdist3(b0.x - fx, b0.y - fy, b0.z - fz);
-          const int id = f * NBOX + k;
-          cnt += (v < t) || (v == t && id < pi);
-        }
-      } else {
+      for (int c = 0; c < ncand; c++) {
+        int cnt = 0;
+        const float t = w.cand.cd2[c];
+        const int pi = w.cand.pair[c];
 #pragma unroll 1
         for (int k = lane; k < nb; k += 32) {
           const float4 b0 = ldg4(bp + 2 * k);
@@ -642,44 +663,46 @@ DEV void collide_boxes(WS& w, const EnvBuffers& B, int env, int lane, bool build
             cnt += (v < t) || (v == t && id < pi);
           }
         }
+        cnt = warp_sum_i(cnt);
+        if (lane == c) mycnt = cnt;
       }
-      cnt = warp_sum_i(cnt);
-      if (lane == c) mycnt = cnt;
     }
   }
-  // keep the max_contact_points deepest of the surviving pairs (ties -> broad-phase order, then slot order)
-  const float inf = __int_as_float(0x7f800000);
+  // keep the max_contact_points deepest of the surviving pairs (ties -> broad-phase order, then slot order): every
+  // candidate counts the candidates that precede it in that order; the first max_contact_points fill the box slots, all
+  // at once (each winner computes its own contact frame)
   const bool mine = lane < ncand && !(cull && mycnt >= GC.max_geom_pairs);
-  float myd = mine ? w.cand.dist[lane] : inf;
+  const float myd = mine ? w.cand.dist[lane] : inf;
   const int mypair = w.cand.pair[lane < ncand ? lane : 0];
   const int maxc = GC.max_contact_points < 4 ? GC.max_contact_points : 4;
+  syncwarp();
+  if (lane < ncand) { w.cand.dist[lane] = myd; w.cand.cd2[lane] = __int_as_float(mycnt); }
+  syncwarp();
+  int order = 0;
 #pragma unroll 1
-  for (int s = 0; s < maxc; s++) {
-    const float dmin = warp_min(myd);
-    if (all_lanes(dmin == inf)) break;
-    const bool tie = (myd == dmin);
-    const int cm = warp_min_i(tie ? mycnt : 0x7fffffff);
-    const unsigned win = wballot(tie && mycnt == cm);
-    if (lane == ffs_(win) - 1) {
-      const int c = 4 + s, f = mypair / NBOX, k = mypair % NBOX;
-      const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
-      const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float l[3], pt[3];
-      const float dist = sphere_box_local(bx, w.foot[f], r, l, pt);
-      float nl[3] = {pt[0] - l[0], pt[1] - l[1], pt[2] - l[2]};
-      const float dn = sqrtf(dot3(nl, nl));
-      if (dn < PGTT_MINVAL) { nl[0] = nl[1] = nl[2] = 0.f; } else { nl[0] /= dn; nl[1] /= dn; nl[2] /= dn; }
-      // contact point: midway between the box point and the sphere surface point
-      const float pl0 = 0.5f * (pt[0] + l[0] + nl[0] * r), pl1 = 0.5f * (pt[1] + l[1] + nl[1] * r), pl2 = 0.5f * (pt[2] + l[2] + nl[2] * r);
-      float nw[3] = {bx[6] * nl[0] - bx[7] * nl[1], bx[7] * nl[0] + bx[6] * nl[1], nl[2]};
-      w.c_pos[c][0] = bx[0] + bx[6] * pl0 - bx[7] * pl1;
-      w.c_pos[c][1] = bx[1] + bx[7] * pl0 + bx[6] * pl1;
-      w.c_pos[c][2] = bx[2] + pl2;
-      make_frame(w.c_frame[c], nw);
-      w.c_dist[c] = dist; w.c_leg[c] = f; w.c_box[c] = k;
-      w.c_mu[c] = fmaxf(GC.foot_mu, B.m_boxfric[env * NBOX + k]);
-      myd = inf;
-    }
+  for (int c = 0; c < ncand; c++) {
+    const float d = w.cand.dist[c];
+    const int n = __float_as_int(w.cand.cd2[c]);
+    order += (d < myd) || (d == myd && (n < mycnt || (n == mycnt && c < lane)));
+  }
+  if (mine && order < maxc) {
+    const int c = 4 + order, f = mypair / NBOX, k = mypair % NBOX;
+    const float4 b0 = ldg4(bp + 2 * k), b1 = ldg4(bp + 2 * k + 1);
+    const float bx[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float l[3], pt[3];
+    const float dist = sphere_box_local(bx, w.foot[f], r, l, pt);
+    float nl[3] = {pt[0] - l[0], pt[1] - l[1], pt[2] - l[2]};
+    const float dn = sqrtf(dot3(nl, nl));
+    if (dn < PGTT_MINVAL) { nl[0] = nl[1] = nl[2] = 0.f; } else { nl[0] /= dn; nl[1] /= dn; nl[2] /= dn; }
+    // contact point: midway between the box point and the sphere surface point
+    const float pl0 = 0.5f * (pt[0] + l[0] + nl[0] * r), pl1 = 0.5f * (pt[1] + l[1] + nl[1] * r), pl2 = 0.5f * (pt[2] + l[2] + nl[2] * r);
+    float nw[3] = {bx[6] * nl[0] - bx[7] * nl[1], bx[7] * nl[0] + bx[6] * nl[1], nl[2]};
+    w.c_pos[c][0] = bx[0] + bx[6] * pl0 - bx[7] * pl1;
+    w.c_pos[c][1] = bx[1] + bx[7] * pl0 + bx[6] * pl1;
+    w.c_pos[c][2] = bx[2] + pl2;
+    make_frame(w.c_frame[c], nw);
+    w.c_dist[c] = dist; w.c_leg[c] = f; w.c_box[c] = k;
+    w.c_mu[c] = fmaxf(GC.foot_mu, B.m_boxfric[env * NBOX + k]);
   }
 }
 
@@ -698,6 +721,7 @@ DEV void collision(WS& w, const EnvBuffers& B, int env, int lane, bool build_lis
   }
   const int nb = GC.n_boxes;
   if (nb > 0) collide_boxes(w, B, env, lane, build_lists);
+  STAGE_TRACE(w, lane);   // collision work done, before its barrier
   stage_sync(w, ST_COLLIDE);
 }
 
@@ -1060,6 +1084,7 @@ DEV int solve(WS& w, Rows& R, int lane) {
     niter++;
   }
   if (lane < NV) w.warm[lane] = w.qacc[lane];
+  STAGE_TRACE(w, lane);   // 5: solver done, before the barrier
   stage_sync(w, ST_POSTSOLVE);
   return niter;
 }
@@ -1122,18 +1147,26 @@ DEV void sensors(WS& w, int lane) {
 // mjx.forward and the Euler update
 // ----------------------------------------------------------------------------------------------
 DEV int forward(WS& w, const EnvBuffers& B, int env, int lane, bool with_sensors, bool build_lists) {
+  // fixed-duration stages first, then the two whose duration depends on the env (collision: number of penetrating
+  // boxes; solver: Newton iterations) back to back, so that the lockstep CTA waits once per substep, not twice
+  STAGE_TRACE(w, lane);   // 0
   kinematics(w, lane);
-  collision(w, B, env, lane, build_lists);   // before the inertia stages: its scratch aliases w.crb
   com_inertia_cdof(w, lane);
   crb_and_inertia(w, lane);
+  STAGE_TRACE(w, lane);   // 1: position stage done
   velocity_rne(w, lane);
   smooth_forces(w, lane);
+  STAGE_TRACE(w, lane);   // 2: velocity stage done
+  collision(w, B, env, lane, build_lists);   // after the inertia stages: its scratch aliases w.crb
+  STAGE_TRACE(w, lane);   // 3: collision done (incl. its barrier, if enabled)
   Rows R;
   make_rows(w, R, lane);
   arrow_factor(w, w.MB, w.MC, w.MA, lane);
   arrow_solve(w, w.qs, w.qas, lane);
   stage_sync(w, ST_PRESOLVE);
+  STAGE_TRACE(w, lane);   // 4: rows + smooth solve done
   const int niter = solve(w, R, lane);
+  STAGE_TRACE(w, lane);   // 6: after the post-solver barrier (5 is taken inside solve(), before the barrier)
   if (with_sensors) sensors(w, lane);
   return niter;
 }

@@ -114,6 +114,8 @@ struct WS {
   float sens[NSENSOR];
   int niter[4];
   int bar_threads;  // threads of this CTA that take part in stage barriers (32 x live warps)
+  int tix;          // next slot of the stage-timestamp trace (development aid, tools/stage_trace.py)
+  long long* trace; // null in normal launches
   union {
     struct {        // position / velocity stage (index 0 = base, 1+3g+t = leg g link t)
       float xpos[NB][3], xmat[NB][9], xipos[NB][3];

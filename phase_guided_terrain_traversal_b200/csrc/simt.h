@@ -39,9 +39,22 @@ DEV float4 ldg4(const float4* p) { return __ldg(p); }
 DEV int popc(unsigned x) { return __popc(x); }
 DEV int ffs_(unsigned x) { return __ffs((int)x); }
 DEV float rsqrt_(float x) { return rsqrtf(x); }
-// one out-of-line copy of the accurate sincosf (its range-reduction slow path is ~100 instructions per inlined site)
-DEV_NOINLINE float2 sincos2_(float a) { float2 r; sincosf(a, &r.x, &r.y); return r; }
-DEV void sincos_(float a, float* s, float* c) { const float2 r = sincos2_(a); *s = r.x; *c = r.y; }
+// sin and cos together: Cody-Waite reduction by pi/2 (three-constant split, exact products for |a| < 1e5 - the arguments
+// here are joint angles, yaws and half rotation angles) and the Cephes single-precision kernels on [-pi/4, pi/4]
+// (~1 ulp). ~25 instructions inline; the library sincosf costs ~110 per call plus a 100-instruction slow path per site.
+DEV void sincos_(float a, float* s, float* c) {
+  const float k = rintf(a * 0.636619772367581f);
+  float r = fmaf(k, -1.5703125f, a);
+  r = fmaf(k, -4.837512969970703125e-4f, r);
+  r = fmaf(k, -7.54978995489188e-8f, r);
+  const float r2 = r * r;
+  float sn = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  float cs = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2, fmaf(-0.5f, r2, 1.0f));
+  const int q = (int)k;
+  if (q & 1) { const float t = sn; sn = cs; cs = -t; }
+  if (q & 2) { sn = -sn; cs = -cs; }
+  *s = sn; *c = cs;
+}
 // un-contracted multiply-add: random draws must not depend on whether the compiler forms an FMA
 DEV float mul_add_nofma(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
 #endif
