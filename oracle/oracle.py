@@ -30,13 +30,18 @@ def build(force: bool = False) -> None:
 
 
 def build_native() -> Path:
-    """fp32 oracle compiled for THIS host (-O3 -march=native): the CPU-baseline build of bench.py.
-    Always rebuilt (a library built on another machine may use instructions this CPU lacks)."""
+    """fp32 oracle compiled for THIS host (-O3 -march=native): the CPU-baseline build of bench.py. Built in-tree
+    (oracle/_build/liborc_f32_native.so, git-ignored) so that whoever audits the process sees which library the CPU arm
+    ran. Always rebuilt (a library built on another machine may use instructions this CPU lacks); written under a
+    temporary name and renamed, so concurrent builders never load a half-written file."""
     import os
-    import tempfile
-    out = Path(tempfile.gettempdir()) / f"liborc_f32_native_{os.getpid()}.so"
-    subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-fopenmp", "-std=gnu11", "-DORC_F32", "-o", str(out),
+    bdir = HERE / "_build"
+    bdir.mkdir(exist_ok=True)
+    out = bdir / "liborc_f32_native.so"
+    tmp = bdir / f".liborc_f32_native_{os.getpid()}.so"
+    subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-fopenmp", "-std=gnu11", "-DORC_F32", "-o", str(tmp),
                     str(HERE / "pgtt_oracle.c"), "-lm"], check=True, capture_output=True)
+    os.replace(tmp, out)
     return out
 
 
@@ -92,7 +97,7 @@ def pack_model(m, n_model_bodies: int | None = None) -> np.ndarray:
         m.act_dof, m.act_gainprm[:, 0], m.act_biasprm, m.act_ctrlrange, m.act_forcerange,
         m.foot_body, m.foot_geom_id, m.foot_pos, [m.foot_radius], m.foot_friction, m.foot_solref, m.foot_solimp, [m.foot_margin],
         [m.floor_geom_id, m.box_geom_id0], m.floor_friction, m.floor_solref, m.floor_solimp,
-        [m.box_rbound], [0.02, 1.0], [0.9, 0.95, 0.001, 0.5, 2.0], m.box_friction,
+        [m.box_rbound], getattr(m, "box_solref", [0.02, 1.0]), getattr(m, "box_solimp", [0.9, 0.95, 0.001, 0.5, 2.0]), m.box_friction,
         park[:, 0:3], park[:, 3:7], park[:, 7:10], m.imu_pos,
         [n_model_bodies if n_model_bodies is not None else 14 + nb],
     ]

@@ -106,9 +106,9 @@ class AbiEnv:
         nat.check(self.lib, self.lib.pgtt_sync(self.h, self._stream()))
 
     def set_terrain(self, table):
+        from .terrain import validate_terrain
         t = np.ascontiguousarray(table, dtype=np.float32)
-        if t.ndim != 3 or t.shape[1:] != (100, 10):
-            raise ValueError(f"terrain table must be [T,100,10], got {t.shape}")
+        validate_terrain(t)      # shape, finiteness, yaw-only boxes, positive half-sizes: unsupported tables fail loudly
         nat.check(self.lib, self.lib.pgtt_set_terrain_table(self.h, t.ctypes.data, t.shape[0]))
         self.n_terrains = t.shape[0]
 

@@ -1,8 +1,9 @@
 """Success-count evaluation - what training/evaluate.py:188-259 gets out of brax's evaluator:
-`num_eval_envs` (1000) environments run one full episode with the DETERMINISTIC policy (`tanh(loc)`,
-deploy/policy_net.py:64) and an environment counts as a success when its episode ends without a termination, i.e.
-`abs(final termination reward) < 0.5` (evaluate.py:220-222). Also reports the brax evaluator's episode reward
-mean / std, average episode length and the velocity-tracking percentages evaluate.py:214-215 derives.
+`num_eval_envs` (1000) environments run one full episode with the command ranges of training/evaluate.py:127-129
+(`eval_overrides`: +-[0.4, 0.4, 0.7]) and an environment counts as a success when its episode ends without a termination,
+i.e. `abs(final termination reward) < 0.5` (evaluate.py:220-222). The reference evaluates through brax `ppo.train`, whose
+default is `deterministic_eval=False` - SAMPLED actions - so that is the default here; `--deterministic` evaluates
+`tanh(loc)` as deploy/policy_net.py:64 does. Also reports the evaluator's episode reward mean / std and episode length.
 
     python -m phase_guided_terrain_traversal_b200.evaluate --policy /path/to/policy177 --task_name stairs --terrain_file level07
 """
@@ -15,9 +16,11 @@ from typing import Dict, Optional
 import numpy as np
 
 
-def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 20, seed: int = 0, collect_obs_stats: bool = False) -> Dict:
+def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 20, seed: int = 0, collect_obs_stats: bool = False,
+             deterministic: bool = True) -> Dict:
     """`wenv`: a freshly reset `wrapper.TrainingEnv` (its episode_length must equal `episode_length`); `policy_net`: a
-    `policy.PolicyNet` with parameters. Runs ceil(episode_length / unroll_length) deterministic unrolls on the device."""
+    `policy.PolicyNet` with parameters. Runs ceil(episode_length / unroll_length) unrolls on the device (`deterministic`:
+    tanh(loc) instead of sampled actions)."""
     import torch
     from .rollout import RolloutCollector
     col = RolloutCollector(wenv, policy_net, unroll_length=unroll_length, seed=seed)
@@ -33,7 +36,7 @@ def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 
     obs_cnt = 0
     steps = 0
     while steps < episode_length:
-        _, ro = col.collect(deterministic=True)
+        _, ro = col.collect(deterministic=deterministic)
         done = 1.0 - ro.discount                                     # [T, N]
         term = done * (1.0 - ro.truncation)
         for t in range(ro.reward.shape[0]):
@@ -74,13 +77,15 @@ def main():
     p.add_argument("--terrain_file", default="level07")
     p.add_argument("--num_eval_envs", type=int, default=1000)
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--deterministic", action="store_true", help="evaluate tanh(loc) (deploy/policy_net.py) instead of sampled actions (brax default)")
+    p.add_argument("--training_ranges", action="store_true", help="command ranges of training/train.py:127-129 instead of evaluate.py:127-129")
     a = p.parse_args()
     from . import policy_io, prng, terrain, wrapper
     from .go2 import joystick, joystick_pgtt, randomize, randomize_simple
-    from .go2.configs import baseline_config, default_config, training_overrides
+    from .go2.configs import baseline_config, default_config, eval_overrides, training_overrides
     from .policy import PolicyNet
     joy, cfg_fn = (joystick_pgtt, default_config) if a.method == "pgtt" else (joystick, baseline_config)
-    cfg = training_overrides(cfg_fn())
+    cfg = (training_overrides if a.training_ranges else eval_overrides)(cfg_fn())
     env = joy.Joystick(task=a.task_name, config=cfg)
     keys = prng.env_keys(a.seed, a.num_eval_envs)
     rfn = functools.partial(randomize.domain_randomize, rng=keys, terrain_matrix=terrain.load_terrain(a.terrain_file)) if a.task_name == "stairs" \
@@ -90,7 +95,7 @@ def main():
     d = policy_io.load_policy(a.policy)
     net = PolicyNet((d["policy"][0][0].shape[0], *[k.shape[1] for k in d["policy"][0]]))
     net.set_params(d["policy"][0], d["policy"][1], d["mean"], d["std"])
-    r = evaluate(wenv, net, episode_length=cfg.episode_length, seed=a.seed)
+    r = evaluate(wenv, net, episode_length=cfg.episode_length, seed=a.seed, deterministic=a.deterministic)
     print({k: v for k, v in r.items() if not (k.startswith("obs_") or k.startswith("priv_"))})
 
 

@@ -70,3 +70,11 @@ def training_overrides(cfg: config_dict.ConfigDict) -> config_dict.ConfigDict:
     cfg.command_config.u_min = [-0.6, -0.6, -1.0]
     cfg.gait_freq = [1, 3]
     return cfg
+
+
+def eval_overrides(cfg: config_dict.ConfigDict) -> config_dict.ConfigDict:
+    """The mutations training/evaluate.py:127-129 applies: narrower command ranges than training."""
+    cfg.command_config.u_max = [0.4, 0.4, 0.7]
+    cfg.command_config.u_min = [-0.4, -0.4, -0.7]
+    cfg.gait_freq = [1, 3]
+    return cfg

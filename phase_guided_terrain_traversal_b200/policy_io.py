@@ -50,9 +50,24 @@ def _reconstruct_array(fun, args, arr_state=None, aval_state=None):
     return np.asarray(v)
 
 
+# The only globals a policy pickle may resolve: numpy array reconstruction and plain containers. Everything else (jax /
+# flax / brax classes, but also builtins.eval, os.system, ...) becomes an inert attribute bag, so a crafted pickle cannot
+# run code through this loader.
+_SAFE_GLOBALS = {
+    ("builtins", "tuple"), ("builtins", "list"), ("builtins", "dict"), ("builtins", "set"), ("builtins", "frozenset"),
+    ("builtins", "slice"), ("builtins", "complex"), ("builtins", "bytearray"), ("builtins", "int"), ("builtins", "float"),
+    ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"),
+    ("collections", "OrderedDict"), ("_codecs", "encode"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float32"), ("numpy", "float64"), ("numpy", "int32"), ("numpy", "int64"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+}
+
+
 class _StubUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.startswith("numpy") or module in ("builtins", "collections", "copyreg", "_codecs"):
+        if (module, name) in _SAFE_GLOBALS:
             return super().find_class(module, name)
         if name == "_reconstruct_array":
             return _reconstruct_array
@@ -79,9 +94,9 @@ def load_policy(path):
         out["policy"] = _layers(net["policy"])
         if net.get("value") is not None:
             out["value"] = _layers(net["value"])
-        if "privileged_state" in norm["mean"]:
-            out["value_mean"] = np.asarray(norm["mean"]["privileged_state"], np.float32)
-            out["value_std"] = np.asarray(norm["std"]["privileged_state"], np.float32)
+    if "privileged_state" in norm["mean"]:    # both layouts carry the value network's input statistics
+        out["value_mean"] = np.asarray(norm["mean"]["privileged_state"], np.float32)
+        out["value_std"] = np.asarray(norm["std"]["privileged_state"], np.float32)
     return out
 
 

@@ -558,6 +558,9 @@ class PPOTrainer:
             for dst, src in zip(self.value_params[0] + self.value_params[1], list(d["value"][0]) + list(d["value"][1])):
                 dst.copy_(torch.as_tensor(src).to(dst))
         cnt = float(d["count"] or 0.0)
+        if cnt > 0 and d.get("value_mean") is None:
+            # value weights trained on normalised inputs would otherwise meet an un-initialised normaliser
+            raise ValueError(f"{path} carries value-network parameters but no privileged_state statistics: cannot resume training from it")
         for rs, mean, std in ((self.norm_state, d["mean"], d["std"]), (self.norm_priv, d.get("value_mean"), d.get("value_std"))):
             if mean is None or cnt <= 0:
                 continue

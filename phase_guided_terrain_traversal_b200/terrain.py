@@ -23,12 +23,22 @@ def load_terrain(name_or_path) -> np.ndarray:
             raise FileNotFoundError(f"terrain file {name_or_path!r} not found (bundled levels: {sorted(x.stem for x in TERRAIN_DIR.glob('*.npz'))})")
         a = np.load(q)["boxes"]
     a = np.ascontiguousarray(a, dtype=np.float32)
-    if a.ndim != 3 or a.shape[1:] != (100, 10):
-        raise ValueError(f"terrain table must have shape [T,100,10], got {a.shape}")
+    validate_terrain(a)
     return a
 
 
 def validate_terrain(a: np.ndarray) -> None:
-    """The kernels support yaw-only box rotations standing on z = 0 (true of every shipped level)."""
+    """What the kernels support (true of every table terrain/generator.py writes): shape [T,100,10], finite values,
+    yaw-only box rotations (quat x = y = 0, non-zero quaternion) and positive half-sizes. The ray grid and the sphere/box
+    collision use only the yaw of a box, so anything else would give silently wrong hits - fail loudly instead."""
+    a = np.asarray(a)
+    if a.ndim != 3 or a.shape[1:] != (100, 10):
+        raise ValueError(f"terrain table must have shape [T,100,10], got {a.shape}")
+    if not np.isfinite(a).all():
+        raise ValueError("terrain table holds non-finite values")
     if np.abs(a[..., 4:6]).max() != 0:
         raise ValueError("only yaw-rotated boxes (quat x = y = 0) are supported")
+    if (np.abs(a[..., 3]) + np.abs(a[..., 6])).min() <= 1e-9:
+        raise ValueError("terrain table holds a zero quaternion")
+    if a[..., 7:10].min() <= 0:
+        raise ValueError("box half-sizes must be positive")

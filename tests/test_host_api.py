@@ -50,6 +50,57 @@ def test_training_overrides_match_train_py():
     assert cfg.command_config.u_max == [0.6, 0.6, 1.0] and cfg.command_config.u_min == [-0.6, -0.6, -1.0] and cfg.gait_freq == [1, 3]
 
 
+def test_eval_overrides_match_evaluate_py():
+    import re
+    from phase_guided_terrain_traversal_b200.go2.configs import default_config, eval_overrides
+    cfg = eval_overrides(default_config())
+    assert list(cfg.command_config.u_max) == [0.4, 0.4, 0.7] and list(cfg.command_config.u_min) == [-0.4, -0.4, -0.7] and list(cfg.gait_freq) == [1, 3]
+    ref = Path("/root/reference/training/evaluate.py")
+    if ref.exists():     # the values above are what the reference script sets (training/evaluate.py:127-129)
+        src = ref.read_text()
+        assert re.search(r"^\s*env_cfg\.command_config\.u_max=\[0\.4,0\.4,0\.7\]", src, re.M) and re.search(r"^\s*env_cfg\.command_config\.u_min=\[-0\.4,-0\.4,-0\.7\]", src, re.M)
+
+
+def test_policy_loader_resolves_no_code_and_keeps_value_statistics(tmp_path):
+    """A policy pickle is third-party input: the loader maps every global but numpy array reconstruction and plain
+    containers to an inert bag (a crafted `builtins.eval` reduce does not run); both checkpoint layouts - the 2-tuple
+    (normaliser, PPONetworkParams) and the 3-tuple (normaliser, policy, value) of e.g. policy3 - return the
+    privileged_state statistics the value network was trained on."""
+    import io
+    import pickle
+    from phase_guided_terrain_traversal_b200 import policy_io
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("__import__('pathlib').Path(%r).write_text('x')" % str(tmp_path / "pwned"),))
+    out = policy_io._StubUnpickler(io.BytesIO(pickle.dumps((Evil(),)))).load()
+    assert not (tmp_path / "pwned").exists() and isinstance(out[0], dict)
+    rng = np.random.default_rng(0)
+    ks = [rng.normal(size=s).astype(np.float32) for s in ((171, 8), (8, 24))]
+    bs = [rng.normal(size=s).astype(np.float32) for s in ((8,), (24,))]
+    vk = [rng.normal(size=s).astype(np.float32) for s in ((215, 8), (8, 1))]
+    vb = [rng.normal(size=s).astype(np.float32) for s in ((8,), (1,))]
+    tree = lambda k, b: {"params": {f"hidden_{i}": {"kernel": k[i], "bias": b[i]} for i in range(2)}}
+    norm = {"mean": {"state": np.zeros(171, np.float32), "privileged_state": np.full(215, 2, np.float32)},
+            "std": {"state": np.ones(171, np.float32), "privileged_state": np.full(215, 3, np.float32)}, "count": np.float64(7)}
+    (tmp_path / "three").write_bytes(pickle.dumps((norm, tree(ks, bs), tree(vk, vb))))
+    d = policy_io.load_policy(tmp_path / "three")
+    assert d["value"] is not None and np.all(d["value_mean"] == 2) and np.all(d["value_std"] == 3) and d["count"] == 7
+
+
+def test_unsupported_terrain_tables_fail_loudly():
+    from phase_guided_terrain_traversal_b200 import terrain
+    t = terrain.load_terrain("level1").copy()
+    terrain.validate_terrain(t)
+    for mut, msg in ((lambda a: a.__setitem__((0, 0, 4), 0.3), "yaw"), (lambda a: a.__setitem__((0, 0, 8), 0.0), "half-sizes"),
+                     (lambda a: a.__setitem__((0, 0, 0), np.nan), "finite"), (lambda a: a.__setitem__((0, 0, slice(3, 7)), 0.0), "quaternion")):
+        b = t.copy(); mut(b)
+        with pytest.raises(ValueError, match=msg):
+            terrain.validate_terrain(b)
+    with pytest.raises(ValueError, match="shape"):
+        terrain.validate_terrain(t[:, :50])
+
+
 def test_registry_call_sequence_of_train_py():
     """register_environment -> get_default_config -> load -> _randomizer / get_domain_randomizer (train.py:116-130,165-170,231)."""
     import functools

@@ -58,6 +58,72 @@ def setup_pair(kind, task, cfg, dyn=True, part=True, seed_hi=7, level="level07",
     return m, orc, env, keys
 
 
+
+# ----------------------------------------------------------------------------------------------
+# explaining integer-bookkeeping differences: a contact / termination flag may only differ between two implementations
+# when the quantity it thresholds is within BORDER of the threshold on the side that crossed it
+# ----------------------------------------------------------------------------------------------
+BORDER = 1e-6
+FLAG_FIELDS = (("contact_flags", "contact"), ("last_contact", "last_contact"), ("first_contact", "first_contact"), ("done", "done"))
+
+
+def kernel_foot_depth(env, m):
+    """[N, 4] (flag order FR FL RR RL): deepest listed contact of each foot (min dist; +inf when the foot has none)."""
+    dist = env.get("contact_dist").astype(np.float64)
+    geom = env.get("contact_geom").reshape(-1, 8, 2)
+    foot_geom = np.where(np.arange(8)[None, :] < 4, geom[:, :, 1], geom[:, :, 0])   # plane slots: (floor, foot); box slots: (foot, box)
+    out = np.full((dist.shape[0], 4), np.inf)
+    for k in range(4):
+        fg = int(m.foot_geom_id[k ^ 1])
+        d = np.where(foot_geom == fg, dist, np.inf)
+        out[:, k] = d.min(1)
+    return out
+
+
+def oracle_foot_depth(orc, idx):
+    out = np.full((len(idx), 4), np.inf)
+    for r, i in enumerate(idx):
+        f, k = orc.contacts(int(i))
+        for c in range(8):
+            if k[c, 3] >= 0:
+                out[r, int(k[c, 3]) ^ 1] = min(out[r, int(k[c, 3]) ^ 1], f[c, 0])
+    return out
+
+
+def assert_flips_are_borderline(tag, differing, contact_a, contact_b, depth_a, depth_b, upz_a, upz_b, done_a, done_b, border=BORDER):
+    """For the envs in `differing` (first step at which their flags differ): every foot whose contact flag differs must have
+    its deepest contact within BORDER of zero on the side that reports contact (and, where the other side lists the pair,
+    there too); a differing `done` needs |up_z| < BORDER; nothing else may differ at that step."""
+    for r, i in enumerate(differing):
+        explained = False
+        for k in range(4):
+            if contact_a[r, k] != contact_b[r, k]:
+                d_in = depth_a[r, k] if contact_a[r, k] else depth_b[r, k]       # the side that says "contact"
+                d_out = depth_b[r, k] if contact_a[r, k] else depth_a[r, k]
+                assert -border < d_in < 0, (tag, int(i), k, "contact flag differs with a depth that is not borderline", d_in, d_out)
+                assert not d_out < 0, (tag, int(i), k, d_in, d_out)   # (the other side may list a different, non-penetrating pair of that foot)
+                explained = True
+        if done_a[r] != done_b[r]:
+            assert abs(upz_a[r]) < border and abs(upz_b[r]) < border, (tag, int(i), "termination differs away from up_z = 0", upz_a[r], upz_b[r])
+            explained = True
+        assert explained, (tag, int(i), "bookkeeping differs without a contact / termination flag at its threshold")
+
+
+def ray_edge_clearance(boxes, xy):
+    """Distance of each ray (x, y) to the nearest footprint edge of any box: a vertical ray can only land on different
+    sides of a box in two implementations when this is ~0."""
+    best = np.full(xy.shape[:-1], np.inf)
+    for b in boxes:
+        cw, sw = b[3] ** 2 - b[6] ** 2, 2 * b[3] * b[6]
+        rel = xy - b[:2]
+        lx, ly = cw * rel[..., 0] + sw * rel[..., 1], -sw * rel[..., 0] + cw * rel[..., 1]
+        ex, ey = np.abs(lx) - b[7], np.abs(ly) - b[8]
+        near_x = np.where(ey <= 1e-5, np.abs(ex), np.inf)     # crossing the x edge while (almost) inside in y
+        near_y = np.where(ex <= 1e-5, np.abs(ey), np.inf)
+        best = np.minimum(best, np.minimum(near_x, near_y))
+    return best
+
+
 @pytest.mark.parametrize("kind", BACKENDS)
 @pytest.mark.parametrize("task,seed,level", [("flat_terrain", 3, None), ("stairs", 3, "level07"), ("stairs", 17, "level13")])
 def test_forward_stage_by_stage(kind, task, seed, level, train_cfg):
@@ -166,8 +232,14 @@ def test_heightscan_matches_oracle_and_numpy(kind, train_cfg):
     hk = np.asarray(env.heightscan(center.astype(np.float32), yaw.astype(np.float32)).cpu() if kind.startswith("cuda") else env.heightscan(center.astype(np.float32), yaw.astype(np.float32)))
     assert np.abs(ho[..., :2] - hk[..., :2]).max() < 1e-5
     dz = np.abs(ho[..., 2] - hk[..., 2])
-    assert (dz < 1e-5).mean() > 0.995     # a ray within 1 ulp of a box edge may land on either side
     assert ho[..., 2].max() > 0.05        # the scans do see boxes
+    table = terr_mod.load_terrain("level13")
+    tidx = orc.get("terrain_index")[:, 0].astype(int)
+    for i in range(N):                    # a ray may only land on the other side of a box when it is within BORDER of its edge
+        miss = dz[i] >= 1e-5
+        if miss.any():
+            assert ray_edge_clearance(table[tidx[i]], hk[i, ..., :2].astype(np.float64))[miss].max() < BORDER, (i, dz[i][miss])
+    assert (dz < 1e-5).mean() > 0.995
     # numpy restatement for env 0
     table = terr_mod.load_terrain("level13")
     boxes = table[int(orc.get("terrain_index")[0, 0])]
@@ -183,7 +255,8 @@ def test_heightscan_matches_oracle_and_numpy(kind, train_cfg):
         lx, ly = cw * rel[..., 0] + sw * rel[..., 1], -sw * rel[..., 0] + cw * rel[..., 1]
         inside = (np.abs(lx) <= b[7]) & (np.abs(ly) <= b[8])
         z = np.where(inside, np.maximum(z, b[2] + b[9]), z)
-    assert (np.abs(z - hk[0, ..., 2]) < 1e-5).mean() > 0.98
+    bad = np.abs(z - hk[0, ..., 2]) >= 1e-5
+    assert bad.mean() < 0.02 and (not bad.any() or ray_edge_clearance(boxes, xy)[bad].max() < BORDER)
 
 
 @pytest.mark.parametrize("kind", BACKENDS)
@@ -217,37 +290,50 @@ def test_autoreset_and_episode_wrapper(kind, train_cfg):
 
 @pytest.mark.gpu
 def test_kernel_generations_agree_at_scale(train_cfg):
-    """warp-per-env vs quad-per-env (near lists) vs quad-per-env (full scans) on 2048 envs of level13 with DR, three
-    wrapped control steps from the same reset: integer bookkeeping agrees env for env (a contact within 1e-7 of its
-    threshold may flip: <= 0.5 % of envs), observations agree to 1e-3 of their scale on the envs that agree."""
-    import os
+    """warp-per-env (near lists / full scans) vs quad-per-env (near lists / full scans) on 2048 envs of level13 with DR,
+    three wrapped control steps from the same reset. Integer bookkeeping agrees env for env; an env may differ from the
+    warp-per-env run only from a step at which one of its contacts is within 1e-6 of its threshold (asserted per env: no
+    unexplained flips), observations agree to 1e-3 of their scale on the envs that agree. The list and full-scan variants
+    of one generation scan different box sets but must produce identical bits."""
     n = 2048
     m = gm.compile_model("stairs")
     table = terr_mod.load_terrain("level13")
     keys = np.stack([np.full(n, 11, dtype=np.uint32), np.arange(n, dtype=np.uint32)], 1)
     rng = np.random.default_rng(3)
     acts = [rng.uniform(-1, 1, (n, 12)).astype(np.float32) for _ in range(3)]
-    outs = {}
-    for kind in ("cuda", "cuda-quad", "cuda-quadfull"):
+    names = ("contact", "last_contact", "first_contact", "done", "step", "steps_until_next_cmd", "rng", "obs_state", "reward", "contact_geom", "sensordata")
+    kinds = ("cuda", "cuda-warpfull", "cuda-quad", "cuda-quadfull")
+    outs = {k: [] for k in kinds}
+    for kind in kinds:
         env = make_env(kind, m, train_cfg, n)
         env.set_terrain(table); env.randomize(keys, True); env.reset(keys + 5)
         for a in acts:
             env.step(a, wrapped=True)
-        outs[kind] = {k: env.get(k).copy() for k in ("contact", "last_contact", "first_contact", "step", "steps_until_next_cmd", "rng", "obs_state", "reward", "contact_geom")}
+            rec = {k: env.get(k).copy() for k in names}
+            rec["depth"] = kernel_foot_depth(env, m)
+            outs[kind].append(rec)
         env.close()
-    ref = outs["cuda"]
-    assert (ref["contact_geom"][:, 8:] >= 0).any()           # box contacts do occur
-    for kind in ("cuda-quad", "cuda-quadfull"):
-        o = outs[kind]
-        for k in ("step", "steps_until_next_cmd", "rng"):
-            assert np.array_equal(o[k], ref[k]), (kind, k)
-        same = np.all(o["contact"] == ref["contact"], 1) & np.all(o["last_contact"] == ref["last_contact"], 1) & np.all(o["first_contact"] == ref["first_contact"], 1)
-        assert same.mean() > 0.995, (kind, same.mean())
-        err = np.abs(o["obs_state"][same] - ref["obs_state"][same]).max(1)
-        assert np.quantile(err, 0.99) < 1e-3 * max(np.abs(ref["obs_state"]).max(), 1.0), (kind, np.quantile(err, 0.99))
-    # the two quad variants scan different box sets but must produce identical bits
-    for k in outs["cuda-quad"]:
-        assert np.array_equal(outs["cuda-quad"][k], outs["cuda-quadfull"][k]), k
+    assert (outs["cuda"][-1]["contact_geom"][:, 8:] >= 0).any()           # box contacts do occur
+    for a_kind, b_kind in (("cuda", "cuda-warpfull"), ("cuda-quad", "cuda-quadfull")):
+        for s in range(3):
+            for k in names:
+                assert np.array_equal(outs[a_kind][s][k], outs[b_kind][s][k]), (a_kind, b_kind, s, k)
+    excused = np.zeros(n, bool)
+    for s in range(3):
+        ref, o = outs["cuda"][s], outs["cuda-quad"][s]
+        for k in ("step", "rng"):
+            assert np.array_equal(o[k], ref[k]), (s, k)
+        same = np.ones(n, bool)
+        for k in ("contact", "last_contact", "first_contact", "done"):
+            same &= np.all(o[k] == ref[k], 1)
+        new = np.nonzero(~same & ~excused)[0]
+        assert_flips_are_borderline(f"warp vs quad step {s}", new, ref["contact"][new], o["contact"][new], ref["depth"][new], o["depth"][new],
+                                    ref["sensordata"][new, 24], o["sensordata"][new, 24], ref["done"][new, 0], o["done"][new, 0])
+        excused |= ~same
+        assert np.array_equal(o["steps_until_next_cmd"][~excused], ref["steps_until_next_cmd"][~excused])
+        err = np.abs(o["obs_state"][~excused] - ref["obs_state"][~excused]).max(1)
+        assert np.quantile(err, 0.99) < 1e-3 * max(np.abs(ref["obs_state"]).max(), 1.0), (s, np.quantile(err, 0.99))
+    assert excused.mean() < 0.005, excused.mean()
 
 
 @pytest.mark.gpu
@@ -325,6 +411,22 @@ def test_two_handles_with_different_constants_alternate(train_cfg):
     for env, which in ((a_env, "pgtt_stairs"), (b_env, "baseline_flat")):
         assert np.array_equal(env.get("obs_state"), solo[which][0]) and np.array_equal(env.get("qpos"), solo[which][1]), which
     assert a_env.get("obs_state").shape[1] == 171 and b_env.get("obs_state").shape[1] == 162
+    # the hand-over of the constant table is stream-ordered (cudaStreamWaitEvent + async copy), not a host synchronisation:
+    # the host enqueues 40 alternations far faster than the device executes them
+    import time
+    import torch
+    dev_acts = [torch.as_tensor(a, device="cuda") for a in acts]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for i in range(40):
+        a_env.step_ptr(dev_acts[i % 4].data_ptr(), wrapped=True)
+        b_env.step_ptr(dev_acts[i % 4].data_ptr(), wrapped=True)
+    host_s = time.perf_counter() - t0
+    e1.record(); torch.cuda.synchronize()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    assert host_s < 0.5 * dev_s, (host_s, dev_s)
 
 
 @pytest.mark.gpu
@@ -388,13 +490,75 @@ def test_single_and_ragged_env_counts(kind, n, train_cfg):
         compare_state(orc, env, f"n={n} step{s}")
 
 
+def run_against_oracle(tag, orc, env, m, n, steps, act_rng, tol_scale=1.0, max_excused=0.002, done_count=None, statistical=False):
+    """Wrapped steps of `env` against `orc` with per-env accounting: index bookkeeping is exact for every env; an env is
+    excused from the flag / float comparisons only from a step at which one of its contact (or termination) flags sits
+    within BORDER of its threshold - asserted env by env, so an unexplained flip fails the test. `statistical`: for runs of
+    many steps, where fp32 differences of the two solvers are amplified by contact switching (trajectories
+    diverge chaotically), the float fields must agree for 99 % of the envs instead of for every env, a flag may differ
+    where the depth is within the position tolerance of the run (2e-4 m) instead of 1e-6, and an env whose episode ended at
+    the differing step is excused unseen (its contact list was just overwritten by the restored first state) - all of them
+    still count against `max_excused`."""
+    excused = np.zeros(n, bool)
+    unexplained = []
+    border = 2e-4 if statistical else BORDER
+    for s in range(steps):
+        act = act_rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+        orc.step(act.astype(np.float64)); env.step(act)
+        for a in ("rng", "step"):
+            assert np.array_equal(orc.get(a), env.get(a).astype(np.float64)), (tag, s, a)
+        same = np.ones(n, bool)
+        for a, b in FLAG_FIELDS:
+            same &= np.all(orc.get(a) == env.get(b), 1)
+        new = np.nonzero(~same & ~excused)[0]
+        if statistical:
+            new = new[(env.get("episode_done")[new, 0] == 0) & (orc.get("episode_done")[new, 0] == 0)]
+        if len(new):
+            args_ = (orc.get("contact_flags")[new], env.get("contact")[new], oracle_foot_depth(orc, new), kernel_foot_depth(env, m)[new],
+                     orc.get("sensordata")[new, 24], env.get("sensordata")[new, 24], orc.get("done")[new, 0], env.get("done")[new, 0])
+            if not statistical:
+                assert_flips_are_borderline(f"{tag} step {s}", new, *args_, border)
+            else:
+                # long runs: a DEEP contact can also appear on one side only when two box centres are almost equally far from a
+                # foot - mjx's 25-nearest-centres culling (SURVEY Q3) then ranks them differently after many steps of fp32
+                # drift, and a solve cut off by the 5-iteration cap differs at the 1e-3 level (SURVEY App. A7), which ten
+                # steps of contact switching amplify. Such envs are counted, not excused silently: at most 5 in 1000 per run.
+                for r in range(len(new)):
+                    try:
+                        assert_flips_are_borderline(f"{tag} step {s}", new[r:r + 1], *(x[r:r + 1] for x in args_), border)
+                    except AssertionError:
+                        unexplained.append((s, int(new[r])))
+                assert len(unexplained) <= max(2, n // 200), (tag, unexplained)
+        excused |= ~same
+        ok = ~excused
+        if done_count is not None:
+            done_count += env.get("done")[:, 0]
+        for a in ("steps_until_next_cmd", "steps", "truncation", "episode_done"):
+            assert np.array_equal(orc.get(a)[ok], env.get(a).astype(np.float64)[ok]), (tag, s, a)
+        # qpos: joint angles integrate the solver-limited velocities (2e-3 |qvel| dt per step)
+        for a, b, tol in (("obs_state", "obs_state", 1e-4), ("obs_priv", "obs_privileged", 2e-3), ("reward", "reward", 1e-4), ("qpos", "qpos", 1e-5 if s < 2 else 5e-5)):
+            x, y = orc.get(a)[ok], env.get(b).astype(np.float64)[ok]
+            if a == "obs_state":    # gyro and joint velocities integrate the solver output: solver-limited tolerance (module docstring), like `qvel`
+                vel = np.r_[0:3, 18:30]
+                ev = np.abs(x[:, vel] - y[:, vel]).max(1)
+                ev = np.quantile(ev, 0.99) if statistical else ev.max()
+                assert ev <= tol_scale * 2e-3 * max(np.abs(x[:, vel]).max(), 1.0), (tag, s, "obs_state velocities", ev)
+                x = x.copy(); y = y.copy(); x[:, vel] = 0; y[:, vel] = 0
+            err = np.abs(x - y)
+            worst = np.quantile(err.max(1), 0.99) if statistical else err.max()
+            assert worst <= tol_scale * tol * max(np.abs(x).max(), 1.0), (tag, s, a, worst, np.unravel_index(err.argmax(), err.shape), np.quantile(err.max(1), 0.999))
+    assert excused.mean() <= max_excused, (tag, excused.mean())
+    return excused
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfgname,n,level,dyn", [("config1", 4096, "level1", False), ("config2", 8192, "level07", True)])
 def test_baseline_sizes_against_the_oracle(cfgname, n, level, dyn, train_cfg):
     """BASELINE config[1] / config[2] at their full env counts, with the kernel generation `pgtt_create` selects for them
-    (warp-per-env at 4096, quad-per-env at 8192): randomise + reset + 2 wrapped steps against the fp32 oracle, env for env.
-    Index bookkeeping (rng, counters, terrain index) is exact for every env; contact flags may flip for an env whose foot is
-    within float rounding of the contact threshold (<= 0.2 % of envs); on the others obs / reward meet the 1e-4 bar."""
+    (warp-per-env up to 4144 envs, quad-per-env above): randomise + reset + 2 wrapped steps against the fp32 oracle, env for
+    env. Index bookkeeping (rng, counters, terrain index) is exact for every env; a contact flag may differ only where the
+    contact depth is within 1e-6 of zero (asserted per env: no unexplained flips, <= 0.2 % of envs); on the others obs /
+    reward meet the 1e-4 bar."""
     m = gm.compile_model("stairs")
     table = terr_mod.load_terrain(level)
     keys = keys_for(n, 21)
@@ -404,20 +568,75 @@ def test_baseline_sizes_against_the_oracle(cfgname, n, level, dyn, train_cfg):
     orc.randomize(keys, table, dyn); env.set_terrain(table); env.randomize(keys, dyn)
     assert np.array_equal(orc.get("terrain_index")[:, 0], env.get("terrain_index")[:, 0])
     orc.reset(keys + 2); env.reset(keys + 2)
-    rng = np.random.default_rng(n)
-    for s in range(2):
-        act = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
-        orc.step(act.astype(np.float64)); env.step(act)
-        for a in ("rng", "step", "steps_until_next_cmd"):
-            assert np.array_equal(orc.get(a), env.get(a).astype(np.float64)), (s, a)
-        same = np.ones(n, bool)
-        for a, b in (("contact_flags", "contact"), ("last_contact", "last_contact"), ("first_contact", "first_contact"), ("done", "done")):
-            same &= np.all(orc.get(a) == env.get(b), 1)
-        assert same.mean() >= 0.998, (cfgname, s, same.mean())
-        for a, b, tol in (("obs_state", "obs_state", 1e-4), ("obs_priv", "obs_privileged", 2e-3), ("reward", "reward", 1e-4), ("qpos", "qpos", 1e-5)):
-            x, y = orc.get(a)[same], env.get(b).astype(np.float64)[same]
-            err = np.abs(x - y).max(1)
-            assert err.max() <= tol * max(np.abs(x).max(), 1.0), (cfgname, s, a, err.max(), np.quantile(err, 0.999))
+    run_against_oracle(cfgname, orc, env, m, n, 2, np.random.default_rng(n))
+
+
+@pytest.mark.parametrize("kind", ["emu", "emu-quad"])
+def test_flag_accounting_on_the_emulated_kernels(kind, train_cfg):
+    """The per-env flip accounting of the GPU tests below, exercised on the host-emulated kernels (32 envs, level13, DR)."""
+    n = 32
+    m, orc, env, keys = setup_pair(kind, "stairs", train_cfg, dyn=True, level="level13", n=n)
+    orc.reset(keys + 1); env.reset(keys + 1)
+    cnt = np.zeros(n)
+    run_against_oracle(kind, orc, env, m, n, 3, np.random.default_rng(7), max_excused=1 / 32, done_count=cnt)
+    d = kernel_foot_depth(env, m)
+    o = oracle_foot_depth(orc, np.arange(n))
+    both = (d < 0) & (o < 0)     # the kernels list box contacts only while they penetrate
+    assert both.any() and np.abs(d[both] - o[both]).max() < 1e-5 and np.array_equal(d < 0, o < 0)
+
+
+ALL_LEVELS = ["level01", "level02", "level03", "level04", "level05", "level06", "level07", "level08", "level09", "level10",
+              "level1", "level2", "level3", "level4", "level7", "level13"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cuda", "cuda-quad"])
+@pytest.mark.parametrize("level", ALL_LEVELS)
+def test_every_shipped_terrain_file_against_the_oracle(kind, level, train_cfg):
+    """All 16 terrains/level*.npy tables the reference ships (BASELINE config[3] is level01 - level10), both kernel
+    generations: 64 envs with dynamics DR, reset + 3 wrapped steps against the oracle, every State / info field."""
+    n = 64
+    m = gm.compile_model("stairs")
+    table = terr_mod.load_terrain(level)
+    keys = keys_for(n, 40 + ALL_LEVELS.index(level))
+    orc = Oracle(m, train_cfg, n, "f32")
+    env = make_env(kind, m, train_cfg, n)
+    orc.randomize(keys, table, True); env.set_terrain(table); env.randomize(keys, True)
+    assert np.array_equal(orc.get("terrain_index")[:, 0], env.get("terrain_index")[:, 0])
+    orc.reset(keys + 1); env.reset(keys + 1)
+    compare_state(orc, env, f"{level} reset")
+    run_against_oracle(f"{kind} {level}", orc, env, m, n, 3, np.random.default_rng(7), max_excused=2 / 64)
+    assert (env.get("contact_geom")[:, 8:] >= 0).any() or level in ("level01", "level1")   # box contacts occur on the higher levels
+
+
+@pytest.mark.gpu
+def test_auto_reset_bookkeeping_at_baseline_size(train_cfg):
+    """BASELINE config[1] size, 50 wrapped steps with episodes of 12 steps and a tenth of the robots started upside
+    down: every env auto-resets by truncation four times (and the flipped ones by termination at once), i.e. far more
+    than 5 % of the envs go through the restore path; rng, counters, truncation / done flags and the observations after
+    each restore match the oracle env for env (flags may only differ where a contact is borderline, asserted)."""
+    from phase_guided_terrain_traversal_b200.go2.configs import default_config, training_overrides
+    cfg = training_overrides(default_config())
+    cfg.episode_length = 12
+    n = 4096
+    m = gm.compile_model("stairs")
+    table = terr_mod.load_terrain("level1")
+    keys = keys_for(n, 23)
+    orc = Oracle(m, cfg, n, "f32")
+    env = make_env("cuda-auto", m, cfg, n)
+    orc.randomize(keys, table, False); env.set_terrain(table); env.randomize(keys, False)
+    orc.reset(keys + 4); env.reset(keys + 4)
+    q = orc.get("qpos"); q[::10, 3:7] = [0, 1, 0, 0]; q[::10, 2] += 0.3
+    orc.set("qpos", q); env.set("qpos", q.astype(np.float32))
+    resets = np.zeros(n)
+    rng = np.random.default_rng(1)
+    excused = np.zeros(n, bool)
+    for chunk in range(5):
+        excused |= run_against_oracle(f"auto-reset chunk {chunk}", orc, env, m, n, 10, rng, tol_scale=5.0, max_excused=0.02, done_count=resets, statistical=True)
+    assert (env.get("step")[:, 0] == 50).all()
+    steps = env.get("steps")[:, 0]
+    assert ((steps >= 0) & (steps <= 12)).all()
+    assert (resets >= 4).mean() > 0.95 and (resets[::10] >= 5).mean() > 0.9     # four truncations each, one more termination for the flipped ones
 
 
 @pytest.mark.gpu

@@ -125,6 +125,61 @@ def test_rollout_collector_shapes_and_consistency(train_cfg):
 
 
 @pytest.mark.gpu
+def test_rollouts_of_two_envs_with_different_configs_alternate(train_cfg):
+    """Two handles on one device (a phase-guided stairs env, 171 observations, and a baseline flat env, 162 - as train + eval
+    envs of training/train.py:242-263 would be) collected alternately through their CUDA-graphed rollouts: each reproduces its
+    solo run bit for bit, i.e. a graph replay never runs with the other handle's constant table; a handle re-created with
+    the same buffers does not inherit the old graph."""
+    import functools
+    import torch
+    from phase_guided_terrain_traversal_b200 import prng, terrain
+    from phase_guided_terrain_traversal_b200.go2 import joystick, joystick_pgtt, randomize, randomize_simple
+    from phase_guided_terrain_traversal_b200.go2.configs import baseline_config, training_overrides
+    from phase_guided_terrain_traversal_b200.policy import PolicyNet
+    from phase_guided_terrain_traversal_b200.rollout import RolloutCollector
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+    n, T = 96, 5
+    keys = prng.env_keys(8, n)
+
+    def make(which):
+        if which == "a":
+            env = joystick_pgtt.Joystick(task="stairs", config=train_cfg)
+            rfn = functools.partial(randomize.domain_randomize, rng=keys, terrain_matrix=terrain.load_terrain("level07"))
+            net = PolicyNet().init_random(3)
+        else:
+            env = joystick.Joystick(task="flat_terrain", config=training_overrides(baseline_config()))
+            rfn = functools.partial(randomize_simple.domain_randomize, rng=keys)
+            net = PolicyNet((162, 512, 256, 128, 24)).init_random(4)
+        wenv = wrap_for_brax_training(env, episode_length=1000, randomization_fn=rfn)
+        wenv.reset(keys + np.uint32(1))
+        return wenv, RolloutCollector(wenv, net, unroll_length=T, seed=2)
+
+    def run(col, k):
+        out = []
+        for _ in range(k):
+            _, ro = col.collect()
+            out.append((ro.obs_state.clone(), ro.reward.clone(), ro.action.clone()))
+        torch.cuda.synchronize()
+        return out
+
+    solo = {}
+    for which in ("a", "b"):
+        wenv, col = make(which)
+        solo[which] = run(col, 3)
+        del col, wenv
+    (wa, ca), (wb, cb) = make("a"), make("b")
+    got = {"a": [], "b": []}
+    for _ in range(3):
+        got["a"] += run(ca, 1)
+        got["b"] += run(cb, 1)
+    for which in ("a", "b"):
+        for x, y in zip(got[which], solo[which]):
+            for u, v in zip(x, y):
+                assert torch.equal(u, v), which
+    assert got["a"][0][0].shape[-1] == 171 and got["b"][0][0].shape[-1] == 162
+
+
+@pytest.mark.gpu
 def test_evaluator_closed_loop_with_a_reference_policy(train_cfg):
     """training/evaluate.py semantics (success = episode ends without termination) and a closed-loop plausibility pin
     (SURVEY 8c-3): policy177, trained by the reference in real MJX, walks in this env - measured on B200: level07, 1000
