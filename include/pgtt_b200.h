@@ -228,6 +228,26 @@ int pgtt_adam_clip(float* param, const float* grad, float* m, float* v, float* s
                    float beta2, float eps, float max_norm, float grad_scale, void* stream);
 int pgtt_adam_scratch_floats(void);
 
+/* Dense layers of the learner's MLPs (policy 171-512-256-128-24, value 215-512-256-128-1; brax ppo networks as configured by
+ * training/train.py:135-161), hand-written tcgen05 GEMMs with fp32-level accuracy: every fp32 operand is split into two
+ * bf16 parts (hi + lo) and a k-slice issues three bf16 MMAs (hi hi + hi lo + lo hi) with fp32 accumulation in TMEM - ~16
+ * mantissa bits per product (the reference runs these at jax_default_matmul_precision=highest, training/train.py:93-94).
+ * All pointers DEVICE fp32, row-major. w [K][N] is the flax `kernel` ([in, out]); x rows may be padded (ldx >= K).
+ *   forward:         y [M][N] = x [M][:K] w + b;  silu != 0: z receives the pre-activation and y = z * sigmoid(z)
+ *   backward_input:  dx [M][:K] (row stride lddx) = dy [M][N] w^T; z_in != NULL ([M][lddx], the pre-activation whose SiLU is this
+ *                    layer's input): dx is multiplied by SiLU'(z_in) in the epilogue, i.e. it is the gradient wrt z_in
+ *   backward_params: dw [K][N] = x^T dy and db [N] = column sums of dy (may be NULL), from one GEMM launch (the loader threads
+ *                    of the dy operand also sum what they load): the M rows are split over CTAs, the split partials in
+ *                    `scratch` (pgtt_linear_backward_params_scratch(M, K, N) floats) are summed in a fixed order: deterministic
+ *   silu_backward:   dz = dy * silu'(z), elementwise over n values */
+const char* pgtt_learner_last_error(void);
+int pgtt_linear_forward(const float* x, int ldx, const float* w, const float* b, int M, int K, int N, int silu, float* y, float* z, void* stream);
+int pgtt_linear_backward_input(const float* dy, const float* w, int M, int K, int N, float* dx, int lddx, const float* z_in, void* stream);
+int pgtt_linear_backward_params_splits(int M);
+long long pgtt_linear_backward_params_scratch(int M, int K, int N);
+int pgtt_linear_backward_params(const float* x, int ldx, const float* dy, int M, int K, int N, float* dw, float* db, float* scratch, void* stream);
+int pgtt_silu_backward(const float* dy, const float* z, float* dz, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,6 +207,14 @@ def declare(lib):
         lib.pgtt_ppo_head.argtypes = [vp] * 8 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
         lib.pgtt_adam_clip.argtypes = [vp] * 6 + [C.c_longlong] + [C.c_float] * 6 + [vp]
         lib.pgtt_adam_scratch_floats.restype = C.c_int
+        lib.pgtt_learner_last_error.restype = C.c_char_p
+        lib.pgtt_linear_forward.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        lib.pgtt_linear_backward_input.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp]
+        lib.pgtt_linear_backward_params_splits.argtypes = [C.c_int]
+        lib.pgtt_linear_backward_params_scratch.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.pgtt_linear_backward_params_scratch.restype = C.c_longlong
+        lib.pgtt_linear_backward_params.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.pgtt_silu_backward.argtypes = [vp, vp, vp, C.c_longlong, vp]
     return lib
 
 
@@ -215,6 +223,7 @@ ABI_SYMBOLS = [
     "pgtt_reset", "pgtt_step", "pgtt_step_record", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act",
     "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_ppo_head", "pgtt_adam_clip", "pgtt_adam_scratch_floats",
+    "pgtt_learner_last_error", "pgtt_linear_forward", "pgtt_linear_backward_input", "pgtt_linear_backward_params_splits", "pgtt_linear_backward_params_scratch", "pgtt_linear_backward_params", "pgtt_silu_backward",
 ]
 
 _LIB = None
@@ -227,7 +236,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB_PATH.exists() and LIB_PATH.stat().st_mtime >= newest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "pgtt_api.cu"), str(CSRC / "pgtt_policy.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "pgtt_api.cu"), str(CSRC / "pgtt_policy.cu"), str(CSRC / "pgtt_learner.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise NativeLibraryError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")

@@ -152,7 +152,9 @@ template <int OP>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, ENV_CTAS_PER_SM) pgtt_env_kernel(LaunchArgs a) {
   extern __shared__ float4 smem4[];
   const int wpb = blockDim.x >> 5;
-  const int warp = warp_index(), lane = threadIdx.x & 31;
+  const int warp = warp_index();
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));   // volatile: one register for the whole kernel instead of S2R + LOP3 re-derived at every use
   const int env = blockIdx.x * wpb + warp;
   if (env >= a.B.N) return;   // warp-uniform (warp_index is a broadcast): no collective sees a partial warp
   WS& w = *reinterpret_cast<WS*>(reinterpret_cast<char*>(smem4) + (size_t)warp * WS_BYTES);
@@ -387,6 +389,8 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
   if (m->n_boxes != 0 && m->n_boxes != NBOX) return fail(PGTT_ERR_ARG, "pgtt_create: n_boxes must be 0 (flat) or 100 (stairs)");
   if (t->n_substeps < 1 || t->n_substeps > 4) return fail(PGTT_ERR_ARG, "pgtt_create: n_substeps must be in 1..4");
   if (m->gravity[0] != 0 || m->gravity[1] != 0) return fail(PGTT_ERR_ARG, "pgtt_create: gravity must be along z");
+  if (m->jnt_solimp[4] != 2.0 || m->foot_solimp[4] != 2.0 || m->floor_solimp[4] != 2.0 || (m->n_boxes && m->box_solimp[4] != 2.0))
+    return fail(PGTT_ERR_ARG, "pgtt_create: only solimp power = 2 (the MuJoCo default) is supported");
 #ifndef PGTT_HOST_EMU
   {
     int ndev = 0;

@@ -736,23 +736,17 @@ struct Rows {
   int lactive;
 };
 
-// impedance curve for a general solimp power (never taken by the GO2 model: power = 2)
-DEV_NOINLINE float imp_curve_general(float x, float mid, float power) {
-  return x < mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
-}
-
+// impedance curve: only solimp power = 2 (the MuJoCo default; every geom / joint of the GO2 scenes) is supported -
+// pgtt_create rejects other models, which keeps two powf expansions (~600 instructions) out of the kernel
 DEV void kbi(const float* solref, const float* solimp, float pos, float* k, float* b, float* imp) {
   float timeconst = fmaxf(solref[0], 2.f * GC.dt);
   const float dampratio = solref[1];
   const float dmin = fminf(fmaxf(solimp[0], 1e-4f), 0.9999f), dmax = fminf(fmaxf(solimp[1], 1e-4f), 0.9999f);
   const float width = fmaxf(solimp[2], PGTT_MINVAL), mid = fminf(fmaxf(solimp[3], 1e-4f), 0.9999f);
-  const float power = fmaxf(solimp[4], 1.f);
   *k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
   *b = 2.f / (dmax * timeconst);
   const float x = fabsf(pos) / width;
-  float y;
-  if (power == 2.f) y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-  else y = imp_curve_general(x, mid, power);
+  const float y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
   float im = dmin + y * (dmax - dmin);
   im = fminf(fmaxf(im, dmin), dmax);
   if (x > 1.f) im = dmax;

@@ -243,11 +243,12 @@ DEV void task_step(TaskWS& t, const EnvBuffers& B, const float* action_all, int 
     const int q = lane >> 3, sub = lane & 7;
     const int r0 = (q < 2) ? 0 : 7, r1 = (q < 2) ? 6 : 13, c0 = (q & 1) ? 0 : 7, c1 = (q & 1) ? 6 : 9;
     float mx = -__int_as_float(0x7f800000), mn = __int_as_float(0x7f800000);
-    const int ncol = c1 - c0, ncell = (r1 - r0) * ncol;
-    for (int k = sub; k < ncell; k += 8) {
-      const float z = t.scan[(r0 + k / ncol) * NRAY_W + c0 + k % ncol];
-      mx = fmaxf(mx, z); mn = fminf(mn, z);
+    if (q & 1) {            // left quadrants: 6 rows x 6 columns (compile-time divisors)
+      for (int k = sub; k < 36; k += 8) { const float z = t.scan[(r0 + k / 6) * NRAY_W + c0 + k % 6]; mx = fmaxf(mx, z); mn = fminf(mn, z); }
+    } else {                // right quadrants: 6 rows x 2 columns
+      for (int k = sub; k < 12; k += 8) { const float z = t.scan[(r0 + (k >> 1)) * NRAY_W + c0 + (k & 1)]; mx = fmaxf(mx, z); mn = fminf(mn, z); }
     }
+    (void)r1; (void)c1;
     for (int o = 4; o > 0; o >>= 1) { mx = fmaxf(mx, shfl_xor(mx, o)); mn = fminf(mn, shfl_xor(mn, o)); }
     const float hm = GC.variant ? mx : mx - mn;   // joystick.py:186 vs joystick_pgtt.py:189
     // lane k (< 4) needs quadrant k

@@ -54,6 +54,9 @@ class PPOConfig:                      # names and defaults of training/train.py:
     # learner GEMM precision: "highest" = fp32 like the reference (jax_default_matmul_precision=highest, train.py:94),
     # "high" = TF32 tensor cores (fp32 storage and accumulation, 10-bit mantissa products)
     matmul_precision: str = "highest"
+    # dense layers of both MLPs (forward, input gradient, weight gradient, SiLU) from the hand-written tcgen05 kernels of
+    # csrc/pgtt_learner.cu (split-bf16 products, fp32 accumulation: fp32-grade accuracy); False = torch GEMMs (CPU tests, comparisons)
+    native_mlp: bool = True
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -141,14 +144,94 @@ def _linear():
     return _LINEAR
 
 
+_NATIVE_LINEAR = None
+
+
+def _native_linear():
+    """Dense layer (+ fused SiLU) on the hand-written tcgen05 GEMMs: `pgtt_linear_forward` / `_backward_input` /
+    `_backward_params` / `pgtt_silu_backward` (include/pgtt_b200.h). The parameter gradients run on `aux` (off the critical
+    path of the backward chain) exactly like the torch variant above."""
+    global _NATIVE_LINEAR
+    if _NATIVE_LINEAR is None:
+        import ctypes as C
+        import torch
+        from . import _native as nat
+
+        def chk(lib, rc):
+            if rc:
+                raise nat.PgttError(rc, lib.pgtt_learner_last_error().decode())
+
+        class NativeLinear(torch.autograd.Function):
+            """y = x k + b, optionally followed by SiLU (then the pre-activation z is the second, non-differentiable output).
+            `z_in`: pre-activation of the SiLU that produced x, or None. Convention inside `mlp`: the SiLU derivative of a hidden
+            layer's output is applied by its CONSUMER (fused into the epilogue of the consumer's input-gradient GEMM), so the
+            gradient a layer with `silu` receives is already dL/dz, and the gradient it returns for x is dL/dz_in."""
+
+            @staticmethod
+            def forward(ctx, x, k, b, aux, silu, z_in):
+                lib = nat.load_library()
+                x = x.contiguous()
+                M, ldx = x.shape
+                K, N = k.shape
+                y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+                z = torch.empty((M, N) if silu else (0,), device=x.device, dtype=torch.float32)
+                st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+                chk(lib, lib.pgtt_linear_forward(x.data_ptr(), ldx, k.data_ptr(), b.data_ptr(), M, K, N, int(silu), y.data_ptr(), z.data_ptr() if silu else None, st))
+                ctx.save_for_backward(x, k, z_in if z_in is not None else z.new_empty(0))
+                ctx.aux, ctx.has_zin = aux, z_in is not None
+                ctx.mark_non_differentiable(z)
+                return y, z
+
+            @staticmethod
+            def backward(ctx, g, _gz):
+                lib = nat.load_library()
+                x, k, z_in = ctx.saved_tensors
+                M, ldx = x.shape
+                K, N = k.shape
+                dev = g.device
+                cur = torch.cuda.current_stream(dev)
+                dz = g.contiguous()
+                aux = ctx.aux
+                if aux is not None:
+                    aux.wait_stream(cur)
+                    dz.record_stream(aux); x.record_stream(aux)
+                with torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext():
+                    sa = torch.cuda.current_stream(dev)
+                    gk = torch.empty((K, N), device=dev, dtype=torch.float32)
+                    gb = torch.empty((N,), device=dev, dtype=torch.float32)
+                    scratch = torch.empty(int(lib.pgtt_linear_backward_params_scratch(M, K, N)), device=dev, dtype=torch.float32)
+                    chk(lib, lib.pgtt_linear_backward_params(x.data_ptr(), ldx, dz.data_ptr(), M, K, N, gk.data_ptr(), gb.data_ptr(), scratch.data_ptr(),
+                                                             C.c_void_p(sa.cuda_stream)))
+                    if aux is not None:
+                        gk.record_stream(cur); gb.record_stream(cur)
+                gx = None
+                if ctx.needs_input_grad[0]:
+                    gx = torch.zeros((M, ldx), device=dev, dtype=torch.float32) if ldx != K else torch.empty((M, ldx), device=dev, dtype=torch.float32)
+                    chk(lib, lib.pgtt_linear_backward_input(dz.data_ptr(), k.data_ptr(), M, K, N, gx.data_ptr(), ldx, z_in.data_ptr() if ctx.has_zin else None,
+                                                            C.c_void_p(cur.cuda_stream)))
+                return gx, gk, gb, None, None, None
+        _NATIVE_LINEAR = NativeLinear
+    return _NATIVE_LINEAR
+
+
 def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-def mlp(x, kernels, biases, aux=None):
+def mlp(x, kernels, biases, aux=None, native: bool = False):
     """`aux`: CUDA stream for the parameter-gradient GEMMs of the backward pass (the caller joins it before it reads the
-    gradients); None = everything on the stream of the forward."""
+    gradients); None = everything on the stream of the forward. `native`: the hand-written tcgen05 layers (CUDA fp32 only)."""
     import torch
+    if native and x.is_cuda and x.dtype == torch.float32:
+        lin = _native_linear()
+        lead = x.shape[:-1]
+        h = x.reshape(-1, x.shape[-1])
+        z_prev = None
+        for i, (k, b) in enumerate(zip(kernels, biases)):
+            hidden = i + 1 < len(kernels)
+            h, z = lin.apply(h, k, b, aux, hidden, z_prev)
+            z_prev = z if hidden else None
+        return h.reshape(*lead, kernels[-1].shape[1])
     lin = _linear()
     for i, (k, b) in enumerate(zip(kernels, biases)):
         x = lin.apply(x.reshape(-1, x.shape[-1]), k, b, aux).reshape(*x.shape[:-1], k.shape[1])
@@ -226,13 +309,13 @@ def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_f
         cur = torch.cuda.current_stream(batch["obs"].device)
         side_stream.wait_stream(cur)
         with torch.cuda.stream(side_stream):
-            baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1]).squeeze(-1)   # [T + 1, B]
-        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0])
+            baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1], cfg.native_mlp).squeeze(-1)   # [T + 1, B]
+        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0], cfg.native_mlp)
         cur.wait_stream(side_stream)
         baseline_all.record_stream(cur)
     else:
-        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0])
-        baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1]).squeeze(-1)       # [T + 1, B]
+        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0], cfg.native_mlp)
+        baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1], cfg.native_mlp).squeeze(-1)       # [T + 1, B]
     baseline, bootstrap = baseline_all[:T], baseline_all[T]
     rewards = batch["reward"] * cfg.reward_scaling
     truncation = batch["truncation"]
@@ -386,6 +469,8 @@ class PPOTrainer:
         self._aux = None
         self._data: Dict = {}
         self.metrics: Dict = {}
+        self.learner_kind = ("hand-written tcgen05 dense layers (split-bf16 products, fp32 accumulation; csrc/pgtt_learner.cu) + hand-written GAE / loss-head / clip+Adam kernels"
+                             if cfg.native_mlp else "torch autograd over library GEMMs + hand-written GAE / loss-head / clip+Adam kernels")
         self._sync_policy()
 
     # -- policy kernel <- learner parameters ---------------------------------------------------------------------------------

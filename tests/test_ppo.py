@@ -217,6 +217,49 @@ def test_fused_ppo_head_matches_autograd():
 
 
 @pytest.mark.gpu
+def test_native_tensor_core_layers_match_torch_fp32_through_the_whole_loss():
+    """`PPOConfig.native_mlp`: both MLPs (forward, SiLU, input / weight / bias gradients) on the hand-written tcgen05 layers of
+    csrc/pgtt_learner.cu against torch fp32 GEMMs ('highest', the reference's precision) on the full PPO loss at the
+    reference network sizes and a 5120-transition minibatch: loss terms to 1e-5, every parameter gradient to 1e-4 of its
+    max-norm; with the value network on a side stream and the parameter gradients on auxiliary streams as in training."""
+    import dataclasses
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo
+    torch.set_float32_matmul_precision("highest")
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    T, B = 20, 256
+    r = lambda *s: torch.randn(s, generator=g, device=dev)
+    obs, obs_priv = torch.zeros(T + 1, B, 172, device=dev), torch.zeros(T + 1, B, 216, device=dev)      # zero-padded rows, as the trainer gathers them
+    obs[..., :171] = r(T + 1, B, 171); obs_priv[..., :215] = r(T + 1, B, 215)
+    pol = ppo.lecun_uniform_params([171, 512, 256, 128, 24], g, dev)
+    val = ppo.lecun_uniform_params([215, 512, 256, 128, 1], g, dev)
+    with torch.no_grad():
+        logits = ppo.mlp(obs[:T], *pol)
+        loc, sr = logits.chunk(2, -1)
+        raw = loc + (torch.nn.functional.softplus(sr) + 0.001) * r(T, B, 12)
+        old_lp = ppo.tanh_normal_log_prob(logits, raw) + 0.3 * r(T, B)
+    done = (torch.rand((T, B), generator=g, device=dev) < 0.05).float()
+    batch = {"obs": obs, "obs_priv": obs_priv, "raw_action": raw, "log_prob": old_lp, "reward": r(T, B).abs(), "discount": 1 - done,
+             "truncation": torch.zeros((T, B), device=dev), "eps": r(T, B, 12)}
+    params = pol[0] + pol[1] + val[0] + val[1]
+    out = {}
+    for native in (False, True):
+        cfg = dataclasses.replace(ppo.PPOConfig(), native_mlp=native)
+        streams = (torch.cuda.Stream(dev), (torch.cuda.Stream(dev), torch.cuda.Stream(dev))) if native else (None, (None, None))
+        for p in params:
+            p.grad = None
+        loss, m = ppo.ppo_loss(pol, val, batch, cfg, fused=True, side_stream=streams[0], aux_streams=streams[1])
+        loss.backward()
+        torch.cuda.synchronize()
+        out[native] = ({k: float(v) for k, v in m.items()}, [p.grad.clone() for p in params])
+    for k in out[False][0]:
+        assert abs(out[True][0][k] - out[False][0][k]) <= 1e-5 * max(1.0, abs(out[False][0][k])), (k, out[True][0][k], out[False][0][k])
+    for a, b in zip(out[True][1], out[False][1]):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-6), (a.shape, float((a - b).abs().max()), float(b.abs().max()))
+
+
+@pytest.mark.gpu
 def test_checkpoint_resume_roundtrip(train_cfg, tmp_path):
     """`--checkpoint_folder` semantics: a trainer restored from a saved pickle has the same parameters and observation
     statistics, so its deterministic policy outputs are identical; shipped reference policies restore as well."""
