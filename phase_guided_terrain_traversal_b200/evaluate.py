@@ -17,21 +17,24 @@ import numpy as np
 
 
 def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 20, seed: int = 0, collect_obs_stats: bool = False,
-             deterministic: bool = True) -> Dict:
+             deterministic: bool = True, per_metric: bool = False) -> Dict:
     """`wenv`: a freshly reset `wrapper.TrainingEnv` (its episode_length must equal `episode_length`); `policy_net`: a
     `policy.PolicyNet` with parameters. Runs ceil(episode_length / unroll_length) unrolls on the device (`deterministic`:
-    tanh(loc) instead of sampled actions)."""
+    tanh(loc) instead of sampled actions). `per_metric`: also sum every entry of `State.metrics` over each env's first
+    episode, which is what brax's EvalWrapper keeps and `training/train.py:214-216` reads (`eval/episode_reward/tracking_lin_vel`);
+    the per-step metrics only live in the env's `metrics` buffer, so this mode steps with unroll length 1."""
     import torch
     from .rollout import RolloutCollector
+    if per_metric:
+        unroll_length = 1
     col = RolloutCollector(wenv, policy_net, unroll_length=unroll_length, seed=seed)
     n, dev = col.abi.N, col.abi.torch_device
     alive = torch.ones(n, device=dev)            # still inside the first episode
     terminated = torch.zeros(n, device=dev)
     ep_reward = torch.zeros(n, device=dev)
     ep_len = torch.zeros(n, device=dev)
-    track_lin = torch.zeros(n, device=dev)
-    track_ang = torch.zeros(n, device=dev)
-    metrics = col.abi.buf["metrics"]
+    metrics = col.abi.buf["metrics"]                  # [N, len(METRIC_KEYS)]: the step's State.metrics
+    ep_metrics = torch.zeros_like(metrics) if per_metric else None
     obs_sum = obs_sq = priv_sum = priv_sq = None
     obs_cnt = 0
     steps = 0
@@ -39,6 +42,8 @@ def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 
         _, ro = col.collect(deterministic=deterministic)
         done = 1.0 - ro.discount                                     # [T, N]
         term = done * (1.0 - ro.truncation)
+        if per_metric:                                               # (one step per unroll: `metrics` is this step's)
+            ep_metrics += alive[:, None] * metrics
         for t in range(ro.reward.shape[0]):
             ep_reward += alive * ro.reward[t]
             ep_len += alive
@@ -53,12 +58,15 @@ def evaluate(wenv, policy_net, episode_length: int = 1000, unroll_length: int = 
             priv_sum = pv.sum(0) if priv_sum is None else priv_sum + pv.sum(0)
             priv_sq = (pv * pv).sum(0) if priv_sq is None else priv_sq + (pv * pv).sum(0)
         steps += ro.reward.shape[0]
-    # tracking rewards of the first episode: episode_metrics is reset by the wrapper at episode ends, so accumulate from
-    # the per-step metrics instead when an env is still alive - approximated here by the mean over the run
     success = (terminated < 0.5)
     out = {"num_eval_envs": n, "success_count": int(success.sum().item()), "success_rate": float(success.float().mean().item()),
            "episode_reward": float(ep_reward.mean().item()), "episode_reward_std": float(ep_reward.std(unbiased=False).item()),
            "avg_episode_length": float(ep_len.mean().item())}
+    if per_metric:
+        from .go2.base import METRIC_KEYS
+        mean, std = ep_metrics.mean(0).tolist(), ep_metrics.std(0, unbiased=False).tolist()
+        out["episode_metrics"] = {k: mean[i] for i, k in enumerate(METRIC_KEYS)}
+        out["episode_metrics_std"] = {k: std[i] for i, k in enumerate(METRIC_KEYS)}
     if collect_obs_stats:
         mean = obs_sum / obs_cnt
         out["obs_mean"] = mean.cpu().numpy()

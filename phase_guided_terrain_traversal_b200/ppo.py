@@ -656,10 +656,77 @@ class PPOTrainer:
         self._sync_policy()
 
 
+class Evaluator:
+    """brax `acting.Evaluator` as `ppo.train` drives it (training/train.py:135-161 passes `num_evals`, `eval_env`): `num_eval_envs`
+    (brax default 128) environments of `eval_env`, wrapped and randomised like the training env, run ONE episode with actions
+    sampled from the current policy (`deterministic_eval=False`, the brax default) and report the first-episode sums under the
+    keys `progress` reads (training/train.py:198-216): `eval/episode_reward[_std]`, `eval/episode_reward/<term>` and
+    `eval/avg_episode_length`. The eval env is a second handle on the trainer's device with its own policy-kernel handle."""
+
+    def __init__(self, eval_env, wrap_env_fn, randomization_fn, cfg: PPOConfig, trainer: "PPOTrainer", num_eval_envs: int = 128,
+                 deterministic_eval: bool = False, seed: int = 0):
+        import functools
+        from . import prng
+        self.trainer, self.cfg, self.deterministic, self.seed = trainer, cfg, bool(deterministic_eval), int(seed)
+        self.keys = prng.env_keys(seed * 104729 + 17, int(num_eval_envs))
+        self.wenv = wrap_env_fn(eval_env, episode_length=cfg.episode_length, action_repeat=1,
+                                randomization_fn=functools.partial(randomization_fn, rng=self.keys) if randomization_fn is not None else None)
+        self.net = None
+        self.runs = 0
+
+    def run_evaluation(self, training_metrics: Optional[Dict] = None) -> Dict:
+        import time
+        from .evaluate import evaluate
+        tr = self.trainer
+        t0 = time.time()
+        self.runs += 1
+        self.wenv.reset(self.keys + np.uint32(self.runs))        # brax: a fresh eval key per run
+        if self.net is None:
+            self.net = PolicyNet((tr.abi.nobs, *self.cfg.policy_hidden_layer_sizes, 24), device=tr.abi.device)
+        ks, bs = tr.policy_params
+        if self.cfg.normalize_observations and float(tr.norm_state.count) > 0:
+            self.net.set_params(ks, bs, tr.norm_state.mean.float(), tr.norm_state.std.float())
+        else:
+            self.net.set_params(ks, bs)
+        r = evaluate(self.wenv, self.net, episode_length=self.cfg.episode_length, seed=self.seed + self.runs, deterministic=self.deterministic,
+                     per_metric=True)
+        dt = time.time() - t0
+        m = {"eval/episode_reward": r["episode_reward"], "eval/episode_reward_std": r["episode_reward_std"],
+             "eval/avg_episode_length": r["avg_episode_length"], "eval/epoch_eval_time": dt,
+             "eval/sps": r["num_eval_envs"] * self.cfg.episode_length / max(dt, 1e-9), "eval/success_rate": r["success_rate"]}
+        for k, v in r["episode_metrics"].items():
+            m[f"eval/episode_{k}"] = v
+        for k, v in r["episode_metrics_std"].items():
+            m[f"eval/episode_{k}_std"] = v
+        for k, v in (training_metrics or {}).items():
+            m[f"training/{k}"] = v
+        return m
+
+
+def _rank0_says(stop: bool, trainer: "PPOTrainer") -> bool:
+    """rank 0's decision (evaluate at all? stop early?), made known to every rank: they all must take the same path through the loop."""
+    if trainer.world == 1:
+        return bool(stop)
+    import torch
+    import torch.distributed as dist
+    flag = torch.tensor([1 if stop else 0], dtype=torch.int32, device=trainer.dev)
+    dist.broadcast(flag, src=0, group=trainer.group)
+    return bool(int(flag.item()))
+
+
 def train(environment, wrap_env_fn, randomization_fn, rng_keys, cfg: PPOConfig, progress_fn: Optional[Callable] = None,
-          policy_params_fn: Optional[Callable] = None, num_training_steps: Optional[int] = None, restore_checkpoint_path=None):
-    """Call shape of `ppo.train(environment=..., wrap_env_fn=..., randomization_fn=..., progress_fn=..., ...)` in
-    training/train.py:242-263. `rng_keys`: uint32[N_local, 2] per-env keys of this rank's shard."""
+          policy_params_fn: Optional[Callable] = None, num_training_steps: Optional[int] = None, restore_checkpoint_path=None,
+          eval_env=None, num_evals: int = 1, num_eval_envs: int = 128, deterministic_eval: bool = False):
+    """Call shape of `ppo.train(environment=..., eval_env=..., wrap_env_fn=..., randomization_fn=..., progress_fn=..., ...)` in
+    training/train.py:242-263. `rng_keys`: uint32[N_local, 2] per-env keys of this rank's shard.
+
+    With `eval_env` the schedule is brax's: `num_evals` evaluations (the first one before any training when `num_evals > 1`),
+    `ceil(num_timesteps / ((num_evals - 1) * env_steps_per_training_step))` training steps between two of them; rank 0 evaluates
+    and calls `progress_fn(num_steps, eval_metrics)` then `policy_params_fn`. A truthy return value of `progress_fn` ends
+    training early on every rank - the reference's `progress` returns its convergence verdict (training/train.py:224-229:
+    both tracking rewards above `vel_percentage` of their maximum and the episode reward within 0.5 % of the previous
+    evaluation, or within 0.1 % regardless), which a stock brax would ignore; it is honoured here.
+    Without `eval_env`: `progress_fn(num_steps, training_metrics)` after every training step (no evaluation)."""
     import functools
     wenv = wrap_env_fn(environment, episode_length=cfg.episode_length, action_repeat=1,
                        randomization_fn=functools.partial(randomization_fn, rng=rng_keys) if randomization_fn is not None else None)
@@ -668,11 +735,36 @@ def train(environment, wrap_env_fn, randomization_fn, rng_keys, cfg: PPOConfig, 
     if restore_checkpoint_path is not None:
         trainer.restore(restore_checkpoint_path)
     per_step = cfg.unroll_length * cfg.batch_size * cfg.num_minibatches
-    steps = num_training_steps if num_training_steps is not None else max(1, math.ceil(cfg.num_timesteps / per_step))
-    for it in range(steps):
-        m = trainer.training_step()
+    if not _rank0_says(eval_env is not None, trainer):       # (only rank 0 needs an eval env: brax evaluates on process 0)
+        steps = num_training_steps if num_training_steps is not None else max(1, math.ceil(cfg.num_timesteps / per_step))
+        for it in range(steps):
+            m = trainer.training_step()
+            stop = progress_fn(trainer.env_steps, m) if progress_fn is not None else False
+            if policy_params_fn is not None:
+                policy_params_fn(trainer.env_steps, trainer)
+            if _rank0_says(bool(stop) and trainer.rank == 0, trainer):
+                break
+        return trainer
+    evaluator = Evaluator(eval_env, wrap_env_fn, randomization_fn, cfg, trainer, num_eval_envs, deterministic_eval, cfg.seed) if trainer.rank == 0 else None
+    trainer.stopped_early = False
+    trainer.evaluator = evaluator
+    epochs = max(int(num_evals) - 1, 1)
+    steps_per_epoch = num_training_steps if num_training_steps is not None else max(1, math.ceil(cfg.num_timesteps / (epochs * per_step)))
+    if num_evals > 1 and evaluator is not None:
+        m = evaluator.run_evaluation({})
         if progress_fn is not None:
-            progress_fn(trainer.env_steps, m)
-        if policy_params_fn is not None:
-            policy_params_fn(trainer.env_steps, trainer)
+            progress_fn(0, m)
+    for ep in range(epochs):
+        for it in range(steps_per_epoch):
+            tm = trainer.training_step()
+        stop = False
+        if evaluator is not None:
+            m = evaluator.run_evaluation(tm)
+            if progress_fn is not None:
+                stop = bool(progress_fn(trainer.env_steps, m))
+            if policy_params_fn is not None:
+                policy_params_fn(trainer.env_steps, trainer)
+        if _rank0_says(stop, trainer):
+            trainer.stopped_early = True
+            break
     return trainer

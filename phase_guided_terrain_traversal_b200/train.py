@@ -49,10 +49,28 @@ def run_training(args):
     keys = sharding.shard_keys(args.seed, args.num_envs, rank, world)
     t0 = time.time()
 
-    def progress(num_steps, metrics):                                                                                # train.py:189-229
-        if rank == 0:
-            print(f"steps {num_steps:>12d}  reward/step {metrics['reward_per_step']:.5f}  done-rate {metrics['episode_done_rate']:.4f}  "
-                  f"loss {metrics['total_loss']:.4f}  entropy {metrics['entropy']:.3f}  {num_steps / (time.time() - t0):,.0f} env-steps/s", flush=True)
+    x_data, y_data, y_dataerr, linvels, angvels = [], [], [], [], []                                                # train.py:182-186
+    scales = env_cfg.reward_config.scales
+
+    def progress(num_steps, metrics):                                                                                # train.py:198-229
+        """Called on rank 0 with the evaluator's metrics; returns the reference's convergence verdict (True = stop)."""
+        x_data.append(num_steps)
+        y_data.append(metrics["eval/episode_reward"])
+        y_dataerr.append(metrics["eval/episode_reward_std"])
+        vel_tracking_per = metrics["eval/episode_reward/tracking_lin_vel"] / (scales.tracking_lin_vel * env_cfg.episode_length)
+        ang_tracking_per = metrics["eval/episode_reward/tracking_ang_vel"] / (scales.tracking_ang_vel * env_cfg.episode_length)
+        linvels.append(vel_tracking_per)
+        angvels.append(ang_tracking_per)
+        print(f"steps {num_steps:>12d}  eval reward {y_data[-1]:.3f} +- {y_dataerr[-1]:.3f}  Lin vel {vel_tracking_per:.3f}  ang vel {ang_tracking_per:.3f}  "
+              f"episode length {metrics['eval/avg_episode_length']:.0f}  training reward/step {metrics.get('training/reward_per_step', float('nan')):.5f}  "
+              f"{num_steps / max(time.time() - t0, 1e-9):,.0f} env-steps/s", flush=True)
+        if len(y_data) >= 2 and y_data[-1] != 0:                                                                      # termination criteria, train.py:224-228
+            rel = abs((y_data[-1] - y_data[-2]) / y_data[-1])
+            if vel_tracking_per > env_cfg.vel_percentage and ang_tracking_per > env_cfg.vel_percentage and rel <= 0.005:
+                return True
+            if rel <= 0.001:
+                return True
+        return False
 
     restore = None
     if args.checkpoint_folder is not None:                                                                          # train.py:246-256
@@ -77,8 +95,16 @@ def run_training(args):
         if rank == 0 and ckdir is not None:
             trainer.save(ckdir / f"{num_steps}")
 
-    trainer = ppo.train(environment=env, wrap_env_fn=wrapper.wrap_for_brax_training, randomization_fn=registry.get_domain_randomizer(env_name),
-                        rng_keys=keys, cfg=cfg, progress_fn=progress, policy_params_fn=policy_params_fn, restore_checkpoint_path=restore)
+    trainer = ppo.train(environment=env, eval_env=registry.load(env_name, config=env_cfg) if rank == 0 else None,                    # train.py:242-263
+                        wrap_env_fn=wrapper.wrap_for_brax_training, randomization_fn=registry.get_domain_randomizer(env_name),
+                        rng_keys=keys, cfg=cfg, progress_fn=progress, policy_params_fn=policy_params_fn, restore_checkpoint_path=restore,
+                        num_evals=args.num_evals, num_eval_envs=args.num_eval_envs)
+    if rank == 0 and args.plots:                                                                                      # train.py:267-270
+        from pathlib import Path
+        pl = Path(args.plots)
+        pl.mkdir(parents=True, exist_ok=True)
+        for name, arr in (("mean", y_data), ("std", y_dataerr), ("lin_vel", linvels), ("anf_vel", angvels), ("steps", x_data)):
+            np.save(pl / f"{name}{args.index}", np.asarray(arr))
     if rank == 0 and args.out:
         trainer.save(args.out)                                                                                       # model.save_params, train.py:266
         print(f"saved {args.out} (layout of deploy/policy_net.py:6-33)")
@@ -104,6 +130,10 @@ def main():
     p.add_argument("--learning_rate", type=float, default=3e-4)
     p.add_argument("--num_minibatches", type=int, default=32)
     p.add_argument("--num_timesteps", type=int, default=1)
+    p.add_argument("--num_evals", type=int, default=31, help="evaluations over the run, brax schedule (the first one before training)")
+    p.add_argument("--num_eval_envs", type=int, default=128, help="environments of the in-training evaluator (brax default)")
+    p.add_argument("--index", type=int, default=32, help="suffix of the arrays written to --plots")
+    p.add_argument("--plots", type=str, default=None, help="folder for the evaluation curves (mean / std / lin_vel / anf_vel, train.py:267-270)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--out", type=str, default=None)
     p.add_argument("--checkpoint_folder", type=str, default=None, help="resume from a policy pickle, or from the highest-numbered one in a folder")

@@ -349,3 +349,100 @@ def test_native_clip_adam_matches_torch(max_norm):
     assert float(flat.t) == 6.0
     for p, q in zip(ref, mine):
         assert q.data_ptr() >= flat.flat.data_ptr() and float((p - q).detach().abs().max()) <= 2e-6 * max(float(p.detach().abs().max()), 1.0)
+
+
+def test_train_follows_the_brax_evaluation_schedule_and_honours_the_early_stop(monkeypatch):
+    """`ppo.train` with an eval env: `num_evals` evaluations, the first before any training, ceil(num_timesteps / ((num_evals - 1)
+    * env steps per training step)) training steps between two of them (brax ppo.train as called by training/train.py:242-263), and a
+    truthy `progress_fn` return (the convergence verdict of training/train.py:224-229) ends the run. Trainer and evaluator are stubs:
+    this is the host-side loop only."""
+    from phase_guided_terrain_traversal_b200 import ppo
+    log = []
+
+    class FakeTrainer:
+        world, rank, group, dev = 1, 0, None, "cpu"
+
+        def __init__(self, wenv, state, cfg):
+            self.env_steps, self.cfg = 0, cfg
+
+        def training_step(self):
+            self.env_steps += self.cfg.unroll_length * self.cfg.batch_size * self.cfg.num_minibatches
+            log.append(("train", self.env_steps))
+            return {"reward_per_step": 0.0}
+
+    class FakeEvaluator:
+        def __init__(self, eval_env, wrap_env_fn, randomization_fn, cfg, trainer, num_eval_envs, deterministic_eval, seed):
+            assert eval_env == "eval-env" and num_eval_envs == 128 and deterministic_eval is False
+            self.trainer = trainer
+
+        def run_evaluation(self, training_metrics=None):
+            log.append(("eval", self.trainer.env_steps))
+            return {"eval/episode_reward": float(self.trainer.env_steps)}
+
+    class FakeWrapped:
+        def reset(self, keys):
+            return "state"
+
+    monkeypatch.setattr(ppo, "PPOTrainer", FakeTrainer)
+    monkeypatch.setattr(ppo, "Evaluator", FakeEvaluator)
+    cfg = ppo.PPOConfig(num_envs=64, batch_size=8, num_minibatches=8, unroll_length=20)
+    per = 20 * 8 * 8
+    cfg.num_timesteps = 5 * per            # 3 epochs (num_evals = 4) of ceil(5 / 3) = 2 training steps
+    seen = []
+    ppo.train("env", lambda e, **kw: FakeWrapped(), None, None, cfg, progress_fn=lambda n, m: seen.append((n, m["eval/episode_reward"])) and False,
+              eval_env="eval-env", num_evals=4)
+    assert log == [("eval", 0), ("train", per), ("train", 2 * per), ("eval", 2 * per), ("train", 3 * per), ("train", 4 * per), ("eval", 4 * per),
+                   ("train", 5 * per), ("train", 6 * per), ("eval", 6 * per)]
+    assert seen == [(0, 0.0), (2 * per, 2.0 * per), (4 * per, 4.0 * per), (6 * per, 6.0 * per)]
+    # early stop: the verdict of the second evaluation ends the run; policy_params_fn still saw that evaluation's parameters
+    log.clear()
+    saved = []
+    tr = ppo.train("env", lambda e, **kw: FakeWrapped(), None, None, cfg, progress_fn=lambda n, m: n >= 2 * per, policy_params_fn=lambda n, t: saved.append(n),
+                   eval_env="eval-env", num_evals=4)
+    assert log == [("eval", 0), ("train", per), ("train", 2 * per), ("eval", 2 * per)] and saved == [2 * per] and tr.stopped_early
+    # num_evals = 1: no evaluation before training, one epoch holding every training step, one evaluation at the end
+    log.clear()
+    ppo.train("env", lambda e, **kw: FakeWrapped(), None, None, cfg, eval_env="eval-env", num_evals=1)
+    assert log == [("train", k * per) for k in range(1, 6)] + [("eval", 5 * per)]
+    # without an eval env: progress_fn after every training step, no evaluator
+    log.clear()
+    ppo.train("env", lambda e, **kw: FakeWrapped(), None, None, cfg, progress_fn=lambda n, m: None)
+    assert log == [("train", k * per) for k in range(1, 6)]
+
+
+@pytest.mark.gpu
+def test_in_training_evaluation_reports_the_keys_progress_reads(train_cfg):
+    """The real evaluator on a second env handle next to the training env (training/train.py:242-263 passes `eval_env`): 64 eval envs run one
+    40-step episode with sampled actions; the metrics carry the first-episode sums `progress` divides by scale * episode length
+    (train.py:214-216); the sums are consistent (reward terms add up to the episode reward, nobody exceeds the episode length); and the
+    training env is not disturbed by the interleaved handle (same training metrics as a run without evaluation)."""
+    from phase_guided_terrain_traversal_b200 import ppo, prng
+    from phase_guided_terrain_traversal_b200.go2.base import METRIC_KEYS
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    from phase_guided_terrain_traversal_b200.go2.randomize_simple import domain_randomize
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+    n = 256
+    cfg = ppo.PPOConfig(num_envs=n, batch_size=64, num_minibatches=8, num_updates_per_batch=1, episode_length=40, seed=5, use_cuda_graph=False)
+    cfg.num_timesteps = 2 * 20 * 64 * 8
+    out = {}
+    for with_eval in (True, False):
+        got = []
+        tr = ppo.train(Joystick(task="flat_terrain", config=train_cfg), wrap_for_brax_training, domain_randomize, prng.env_keys(1, n), cfg,
+                       progress_fn=lambda s, m: got.append((s, dict(m))) and False,
+                       eval_env=Joystick(task="flat_terrain", config=train_cfg) if with_eval else None, num_evals=3, num_eval_envs=64)
+        out[with_eval] = (got, dict(tr.metrics))
+    got, _ = out[True]
+    assert [s for s, _ in got] == [0, 20 * 64 * 8, 2 * 20 * 64 * 8]
+    for _, m in got:
+        assert {"eval/episode_reward", "eval/episode_reward_std", "eval/avg_episode_length", "eval/episode_reward/tracking_lin_vel",
+                "eval/episode_reward/tracking_ang_vel"} <= set(m)
+        assert all(math.isfinite(v) for v in m.values())
+        assert 1.0 <= m["eval/avg_episode_length"] <= 40.0
+        assert 0.0 <= m["eval/episode_reward/tracking_lin_vel"] <= 1.0 * 40 and 0.0 <= m["eval/episode_reward/tracking_ang_vel"] <= 0.5 * 40
+    # Joystick.step: reward = clip(sum of the terms * dt, 0, 10000) (go2/joystick_pgtt.py:202): the summed terms bound the reward from above
+    m = got[-1][1]
+    terms = sum(m[f"eval/episode_{k}"] for k in METRIC_KEYS if k.startswith("reward/"))
+    assert m["eval/episode_reward"] >= terms * 0.02 - 1e-3
+    assert "training/reward_per_step" in got[-1][1] and "training/reward_per_step" not in got[0][1]
+    a, b = out[True][1], out[False][1]
+    assert a["env_steps"] == b["env_steps"] and abs(a["reward_per_step"] - b["reward_per_step"]) < 1e-6 and abs(a["total_loss"] - b["total_loss"]) < 1e-4, (a, b)
