@@ -248,6 +248,27 @@ long long pgtt_linear_backward_params_scratch(int M, int K, int N);
 int pgtt_linear_backward_params(const float* x, int ldx, const float* dy, int M, int K, int N, float* dw, float* db, float* scratch, void* stream);
 int pgtt_silu_backward(const float* dy, const float* z, float* dz, long long n, void* stream);
 
+/* Whole-MLP forward / backward of the learner on blocked split-bf16 operands (csrc/pgtt_mlp.cu): what brax's ppo.train
+ * evaluates per SGD step for the policy and the value network (training/train.py:135-161: hidden sizes (512, 256, 128), SiLU,
+ * fp32-grade products as `jax_default_matmul_precision=highest`, train.py:93-94). A handle owns the device workspace for ONE
+ * row count (the minibatch size): blocked copies of the input, of every weight matrix and of every activation / gradient,
+ * the pre-activations, and the split partials of the weight gradients. dims [n_layers + 1] = in, hidden..., out.
+ *   forward:  y [rows][dims[L]] = MLP(x [rows][:dims[0]], row stride ldx);  w[l] [dims[l]][dims[l+1]] (the flax `kernel`), b[l]
+ *   backward: dw[l], db[l] (overwritten) from dy [rows][dims[L]] = dLoss/dy of the LAST forward; parameters unchanged in between.
+ * All pointers DEVICE fp32; launches on `stream`, no host synchronisation (create / destroy excepted). */
+typedef struct pgtt_mlp pgtt_mlp;
+const char* pgtt_mlp_last_error(void);
+int pgtt_mlp_create(int n_layers, const int* dims, int rows, int device, pgtt_mlp** out);
+void pgtt_mlp_destroy(pgtt_mlp* m);
+int pgtt_mlp_rows(const pgtt_mlp* m);
+int pgtt_mlp_forward(pgtt_mlp* m, const float* x, int ldx, const float* const* w, const float* const* b, float* y, void* stream);
+/* forward with the learner's input fused in: row (t, j) of the minibatch = row t * S + idx[j] of the time-major store `data` [T][S][ld]
+ * (idx: DEVICE int64 [mb]; rows = T_used * mb), normalised as (x - mean[c]) * inv_std[c] when both are given (brax running_statistics) */
+int pgtt_mlp_forward_gather(pgtt_mlp* m, const float* data, int ld, int S, const long long* idx, int mb, const float* mean, const float* inv_std,
+                            const float* const* w, const float* const* b, float* y, void* stream);
+int pgtt_mlp_backward(pgtt_mlp* m, const float* dy, float* const* dw, float* const* db, void* stream);
+int pgtt_mlp_debug_trace(pgtt_mlp* m, unsigned long long* out, int max_launches);   /* development aid, see csrc/pgtt_mlp.cu */
+
 #ifdef __cplusplus
 }
 #endif

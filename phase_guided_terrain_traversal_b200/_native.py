@@ -215,6 +215,15 @@ def declare(lib):
         lib.pgtt_linear_backward_params_scratch.restype = C.c_longlong
         lib.pgtt_linear_backward_params.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
         lib.pgtt_silu_backward.argtypes = [vp, vp, vp, C.c_longlong, vp]
+        lib.pgtt_mlp_last_error.restype = C.c_char_p
+        lib.pgtt_mlp_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
+        lib.pgtt_mlp_destroy.argtypes = [vp]
+        lib.pgtt_mlp_destroy.restype = None
+        lib.pgtt_mlp_rows.argtypes = [vp]
+        lib.pgtt_mlp_forward.argtypes = [vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
+        lib.pgtt_mlp_backward.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
+        lib.pgtt_mlp_forward_gather.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp]
+        lib.pgtt_mlp_debug_trace.argtypes = [vp, vp, C.c_int]
     return lib
 
 
@@ -224,6 +233,7 @@ ABI_SYMBOLS = [
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_act",
     "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_ppo_head", "pgtt_adam_clip", "pgtt_adam_scratch_floats",
     "pgtt_learner_last_error", "pgtt_linear_forward", "pgtt_linear_backward_input", "pgtt_linear_backward_params_splits", "pgtt_linear_backward_params_scratch", "pgtt_linear_backward_params", "pgtt_silu_backward",
+    "pgtt_mlp_last_error", "pgtt_mlp_create", "pgtt_mlp_destroy", "pgtt_mlp_rows", "pgtt_mlp_forward", "pgtt_mlp_forward_gather", "pgtt_mlp_backward", "pgtt_mlp_debug_trace",
 ]
 
 _LIB = None
@@ -236,7 +246,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB_PATH.exists() and LIB_PATH.stat().st_mtime >= newest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "pgtt_api.cu"), str(CSRC / "pgtt_policy.cu"), str(CSRC / "pgtt_learner.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "pgtt_api.cu"), str(CSRC / "pgtt_policy.cu"), str(CSRC / "pgtt_learner.cu"), str(CSRC / "pgtt_mlp.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise NativeLibraryError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")

@@ -214,6 +214,110 @@ def _native_linear():
     return _NATIVE_LINEAR
 
 
+@dataclass
+class GatherInput:
+    """A minibatch that is still a recipe: rows (t, j), t < T, j < len(idx), are rows `idx[j]` of time slices of the time-major store
+    `data` [T_full, S, ld]; `mean` / `inv_std` (fp32 [width] or None) normalise on the way in. The whole-MLP node hands it to
+    `pgtt_mlp_forward_gather`, whose input split kernel gathers, normalises and converts in one pass - no gathered or
+    normalised copy of the observations exists."""
+    data: object
+    idx: object
+    T: int
+    width: int
+    mean: object = None
+    inv_std: object = None
+
+    def first(self, T: int) -> "GatherInput":
+        return GatherInput(self.data, self.idx, T, self.width, self.mean, self.inv_std)
+
+    def materialise(self):
+        x = self.data[:self.T].index_select(1, self.idx)[..., :self.width]
+        return (x - self.mean) * self.inv_std if self.mean is not None else x
+
+
+_NATIVE_MLP = None
+_MLP_HANDLES: Dict = {}
+
+
+class _MlpHandle:
+    """One `pgtt_mlp` handle (device workspace for one network at one row count), destroyed with the object."""
+
+    def __init__(self, lib, dims, rows, device):
+        import ctypes as C
+        from . import _native as nat
+        self.lib, self.h = lib, C.c_void_p()
+        rc = lib.pgtt_mlp_create(len(dims) - 1, (C.c_int * len(dims))(*dims), rows, device, C.byref(self.h))
+        if rc:
+            raise nat.PgttError(rc, lib.pgtt_mlp_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.pgtt_mlp_destroy(self.h)
+            self.h = None
+
+
+def _native_mlp():
+    """The whole MLP, forward and backward, on the hand-written blocked split-bf16 tcgen05 GEMMs of csrc/pgtt_mlp.cu
+    (`pgtt_mlp_forward` / `pgtt_mlp_backward`, include/pgtt_b200.h): one autograd node per network. The handle (workspace) is
+    cached per (network = address of its first kernel, widths, rows); it is created outside graph capture by the trainer's
+    eager warm-up steps."""
+    global _NATIVE_MLP
+    if _NATIVE_MLP is None:
+        import ctypes as C
+        import torch
+        from . import _native as nat
+
+        def chk(lib, rc):
+            if rc:
+                raise nat.PgttError(rc, lib.pgtt_mlp_last_error().decode())
+
+        ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+        class NativeMLP(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, n_layers, *params):
+                lib = nat.load_library()
+                ks, bs = params[:n_layers], params[n_layers:]
+                dims = (ks[0].shape[0], *[k.shape[1] for k in ks])
+                gather = isinstance(x, GatherInput)
+                if gather:
+                    dev, rows = x.data.device, x.T * x.idx.numel()
+                    assert x.data.dim() == 3 and x.data.is_contiguous() and x.data.dtype == torch.float32 and x.idx.dtype == torch.int64 and x.width == dims[0]
+                else:
+                    x = x if x.stride(-1) == 1 and x.stride(0) >= x.shape[1] else x.contiguous()
+                    dev, rows = x.device, x.shape[0]
+                key = (ks[0].data_ptr(), dims, rows, dev.index)
+                h = _MLP_HANDLES.get(key)
+                if h is None:
+                    if torch.cuda.is_current_stream_capturing():
+                        raise RuntimeError("pgtt_mlp handle for a new (network, rows) requested inside CUDA graph capture: run one eager step first")
+                    h = _MLP_HANDLES[key] = _MlpHandle(lib, dims, rows, dev.index)
+                y = torch.empty((rows, dims[-1]), device=dev, dtype=torch.float32)
+                st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                if gather:
+                    chk(lib, lib.pgtt_mlp_forward_gather(h.h, x.data.data_ptr(), x.data.shape[2], x.data.shape[1], x.idx.data_ptr(), x.idx.numel(),
+                                                         x.mean.data_ptr() if x.mean is not None else None, x.inv_std.data_ptr() if x.mean is not None else None,
+                                                         ptrs(ks), ptrs(bs), y.data_ptr(), st))
+                else:
+                    chk(lib, lib.pgtt_mlp_forward(h.h, x.data_ptr(), x.stride(0), ptrs(ks), ptrs(bs), y.data_ptr(), st))
+                ctx.h, ctx.n_layers = h, n_layers
+                ctx.save_for_backward(*params)
+                return y
+
+            @staticmethod
+            def backward(ctx, gy):
+                lib = nat.load_library()
+                params = ctx.saved_tensors
+                L = ctx.n_layers
+                gy = gy.contiguous()
+                grads = [torch.empty_like(p) for p in params]
+                st = C.c_void_p(torch.cuda.current_stream(gy.device).cuda_stream)
+                chk(lib, lib.pgtt_mlp_backward(ctx.h.h, gy.data_ptr(), ptrs(grads[:L]), ptrs(grads[L:]), st))
+                return (None, None, *grads)
+        _NATIVE_MLP = NativeMLP
+    return _NATIVE_MLP
+
+
 def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
@@ -222,6 +326,15 @@ def mlp(x, kernels, biases, aux=None, native: bool = False):
     """`aux`: CUDA stream for the parameter-gradient GEMMs of the backward pass (the caller joins it before it reads the
     gradients); None = everything on the stream of the forward. `native`: the hand-written tcgen05 layers (CUDA fp32 only)."""
     import torch
+    if isinstance(x, GatherInput):
+        if native is True:
+            y = _native_mlp().apply(x, len(kernels), *kernels, *biases)
+            return y.reshape(x.T, x.idx.numel(), kernels[-1].shape[1])
+        x = x.materialise()
+    if native and x.is_cuda and x.dtype == torch.float32 and native != "layers":
+        lead = x.shape[:-1]
+        y = _native_mlp().apply(x.reshape(-1, x.shape[-1]), len(kernels), *kernels, *biases)
+        return y.reshape(*lead, kernels[-1].shape[1])
     if native and x.is_cuda and x.dtype == torch.float32:
         lin = _native_linear()
         lead = x.shape[:-1]
@@ -305,25 +418,25 @@ def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_f
     pk, pb = policy_params
     vk, vb = value_params
     T = batch["reward"].shape[0]
+    obs_T = batch["obs"].first(T) if isinstance(batch["obs"], GatherInput) else batch["obs"][:T]
     if side_stream is not None:
-        cur = torch.cuda.current_stream(batch["obs"].device)
+        cur = torch.cuda.current_stream(batch["reward"].device)
         side_stream.wait_stream(cur)
         with torch.cuda.stream(side_stream):
             baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1], cfg.native_mlp).squeeze(-1)   # [T + 1, B]
-        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0], cfg.native_mlp)
+        logits = mlp(obs_T, pk, pb, aux_streams[0], cfg.native_mlp)
         cur.wait_stream(side_stream)
         baseline_all.record_stream(cur)
     else:
-        logits = mlp(batch["obs"][:T], pk, pb, aux_streams[0], cfg.native_mlp)
+        logits = mlp(obs_T, pk, pb, aux_streams[0], cfg.native_mlp)
         baseline_all = mlp(batch["obs_priv"], vk, vb, aux_streams[1], cfg.native_mlp).squeeze(-1)       # [T + 1, B]
     baseline, bootstrap = baseline_all[:T], baseline_all[T]
-    rewards = batch["reward"] * cfg.reward_scaling
     truncation = batch["truncation"]
-    termination = (1.0 - batch["discount"]) * (1.0 - truncation)
-    target_lp = tanh_normal_log_prob(logits, batch["raw_action"])
-    if rewards.is_cuda and rewards.dtype == torch.float32:
+    if batch["reward"].is_cuda and batch["reward"].dtype == torch.float32:
         vs, adv = compute_gae_native(truncation, batch["discount"], batch["reward"], baseline_all.detach(), cfg.gae_lambda, cfg.discounting, cfg.reward_scaling)
     else:
+        rewards = batch["reward"] * cfg.reward_scaling
+        termination = (1.0 - batch["discount"]) * (1.0 - truncation)
         vs, adv = compute_gae(truncation, termination, rewards, baseline.detach(), bootstrap.detach(), cfg.gae_lambda, cfg.discounting)
     if cfg.normalize_advantage:
         if moments_fn is not None:
@@ -337,6 +450,7 @@ def ppo_loss(policy_params, value_params, batch: Dict, cfg: PPOConfig, moments_f
                                    torch.stack([mean, std]).to(torch.float32), cfg.clipping_epsilon, cfg.entropy_cost, 0.001)
         return sums[0], {"total_loss": sums[0].detach(), "policy_loss": sums[1].detach(), "v_loss": sums[2].detach(), "entropy": sums[3].detach()}
     adv = (adv - mean) / (std + 1e-8)
+    target_lp = tanh_normal_log_prob(logits, batch["raw_action"])      # (the fused head computes it itself: not evaluated on that path)
     rho = torch.exp(target_lp - batch["log_prob"])
     s1 = rho * adv
     s2 = torch.clamp(rho, 1.0 - cfg.clipping_epsilon, 1.0 + cfg.clipping_epsilon) * adv
@@ -493,13 +607,16 @@ class PPOTrainer:
         par = self.cfg.parallel_nets
         if par and self._side is None:
             self._side = torch.cuda.Stream(self.dev)
-        if par and self._aux is None:
+        # auxiliary streams carry the parameter-gradient GEMMs of the per-layer paths; the whole-MLP node (native_mlp = True) issues
+        # its weight-gradient GEMMs itself and never forks them (waiting on a stream that was not forked would break a capture)
+        use_aux = par and self.cfg.native_mlp is not True
+        if use_aux and self._aux is None:
             self._aux = (torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev))
         loss, m = ppo_loss(self.policy_params, self.value_params, batch, self.cfg, self._moments, fused=self.cfg.fused_head,
-                           side_stream=self._side if par else None, aux_streams=self._aux if par else (None, None))
+                           side_stream=self._side if par else None, aux_streams=self._aux if use_aux else (None, None))
         self.opt.zero_grad(set_to_none=True)    # backward writes fresh gradients: no fill + accumulate pair per parameter
         loss.backward()
-        if par:   # the parameter-gradient branches rejoin before anything reads the gradients
+        if use_aux:   # the parameter-gradient branches rejoin before anything reads the gradients
             cur = torch.cuda.current_stream(self.dev)
             for a in self._aux:
                 cur.wait_stream(a)
@@ -522,21 +639,28 @@ class PPOTrainer:
         self.opt.step()
         return m
 
+    def _fused_input(self) -> bool:
+        return self.cfg.native_mlp is True
+
     def _minibatch(self):
         """Minibatch `self._mbi` of the current epoch, gathered ON THE DEVICE from the static full-data buffers: the index
         tensors are the only thing the host touches per SGD step, so the whole step (gather, forward, loss, backward,
         clip, Adam) is one graph replay."""
         torch = self.torch
         idx = self._perm.index_select(0, self._mbi).reshape(-1)                          # [mb] segment ids
-        side = None
-        if self.cfg.parallel_nets:     # the value network's input (the largest gather) is fetched on the stream that consumes it
-            if self._side is None:
-                self._side = torch.cuda.Stream(self.dev)
-            side = self._side
-            side.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            batch = {"obs_priv": self._data["obs_priv"].index_select(1, idx)}
-        batch["obs"] = self._data["obs"].index_select(1, idx)
+        if self._fused_input():     # the whole-MLP node gathers, normalises and converts the observations itself (pgtt_mlp_forward_gather)
+            batch = {"obs": GatherInput(self._data["obs"], idx, self.cfg.unroll_length + 1, self.abi.nobs, *self._norm_dev[0]),
+                     "obs_priv": GatherInput(self._data["obs_priv"], idx, self.cfg.unroll_length + 1, self.abi.npriv, *self._norm_dev[1])}
+        else:
+            side = None
+            if self.cfg.parallel_nets:     # the value network's input (the largest gather) is fetched on the stream that consumes it
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self.dev)
+                side = self._side
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                batch = {"obs_priv": self._data["obs_priv"].index_select(1, idx)}
+            batch["obs"] = self._data["obs"].index_select(1, idx)
         batch["raw_action"] = self._data["raw_action"].index_select(1, idx)
         # the four per-transition scalars live in one [4, T, S] buffer: one gather instead of four
         batch.update(zip(_SCALARS, self._scal.index_select(2, idx).unbind(0)))
@@ -591,6 +715,8 @@ class PPOTrainer:
             self._perm = torch.zeros((cfg.num_minibatches, self.mb), dtype=torch.int64, device=self.dev)
             self._eps = f(cfg.num_minibatches, T, self.mb, 12)
             self._mbi = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            nrm = lambda d: (torch.zeros(d, dtype=torch.float32, device=self.dev), torch.ones(d, dtype=torch.float32, device=self.dev))
+            self._norm_dev = (nrm(nobs), nrm(npriv)) if cfg.normalize_observations else ((None, None), (None, None))
         n = self.abi.N
         for u in range(self.unrolls_per_step):
             self.state, ro = self.collector.collect()
@@ -605,8 +731,13 @@ class PPOTrainer:
             obs, priv = data["obs"][..., :self.abi.nobs], data["obs_priv"][..., :self.abi.npriv]
             self.norm_state.update(obs[:T], self.group)
             self.norm_priv.update(priv[:T], self.group)
-            obs.copy_(self.norm_state.normalize(obs))
-            priv.copy_(self.norm_priv.normalize(priv))
+            if self._fused_input():     # raw observations stay in the store; the statistics travel to the input kernel (static buffers: graph replays see them)
+                for (m32, i32), rs in zip(self._norm_dev, (self.norm_state, self.norm_priv)):
+                    m32.copy_(rs.mean)
+                    i32.copy_(1.0 / rs.std)
+            else:
+                obs.copy_(self.norm_state.normalize(obs))
+                priv.copy_(self.norm_priv.normalize(priv))
         last = {}
         for _ in range(cfg.num_updates_per_batch):
             self._perm.copy_(torch.randperm(self.segments, generator=self.gen, device=self.dev).reshape(cfg.num_minibatches, self.mb))

@@ -1,0 +1,3 @@
+set -x
+timeout 600 python -m pytest tests/test_ppo.py tests/test_mlp_native.py -m gpu -q -x 2>&1 | tail -40 | cut -c1-300
+python tools/learner_time.py highest 2>&1 | tail -2
