@@ -54,9 +54,10 @@ class PPOConfig:                      # names and defaults of training/train.py:
     # learner GEMM precision: "highest" = fp32 like the reference (jax_default_matmul_precision=highest, train.py:94),
     # "high" = TF32 tensor cores (fp32 storage and accumulation, 10-bit mantissa products)
     matmul_precision: str = "highest"
-    # dense layers of both MLPs (forward, input gradient, weight gradient, SiLU) from the hand-written tcgen05 kernels of
-    # csrc/pgtt_learner.cu (split-bf16 products, fp32 accumulation: fp32-grade accuracy); False = torch GEMMs (CPU tests, comparisons)
-    native_mlp: bool = True
+    # True: both MLPs, forward and backward, from the hand-written blocked split-bf16 tcgen05 GEMMs of csrc/pgtt_mlp.cu (fp32-grade
+    # accuracy, one autograd node per network); "layers": the per-layer tcgen05 GEMMs of csrc/pgtt_learner.cu; False = torch GEMMs
+    # (CPU tests, comparisons)
+    native_mlp: object = True
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -583,8 +584,11 @@ class PPOTrainer:
         self._aux = None
         self._data: Dict = {}
         self.metrics: Dict = {}
-        self.learner_kind = ("hand-written tcgen05 dense layers (split-bf16 products, fp32 accumulation; csrc/pgtt_learner.cu) + hand-written GAE / loss-head / clip+Adam kernels"
-                             if cfg.native_mlp else "torch autograd over library GEMMs + hand-written GAE / loss-head / clip+Adam kernels")
+        self.learner_kind = {
+            True: "hand-written whole-MLP forward / backward on blocked split-bf16 tcgen05 GEMMs (fp32 accumulation, minibatch gather + normalisation fused into "
+                  "the input kernel; csrc/pgtt_mlp.cu) + hand-written GAE / loss-head / clip+Adam kernels",
+            "layers": "hand-written per-layer tcgen05 GEMMs (split-bf16 products, fp32 accumulation; csrc/pgtt_learner.cu) + hand-written GAE / loss-head / clip+Adam kernels",
+        }.get(cfg.native_mlp, "torch autograd over library GEMMs + hand-written GAE / loss-head / clip+Adam kernels")
         self._sync_policy()
 
     # -- policy kernel <- learner parameters ---------------------------------------------------------------------------------
