@@ -314,9 +314,11 @@ def sub_record(torch, dev, args, cfg, local_rank, rank, world, N, offset, terrai
 
 def train_step_record(torch, dev, cfg, local_rank, rank, world, table, barrier, max_over_ranks, n=4096):
     """One full PPO training step at the reference hyper-parameters (training/train.py:135-161: 2 unrolls of 20 steps, 4 x 32
-    minibatch updates), fp32 ("highest", train.py:93-94), per rank `n` envs; gradients all-reduced when world > 1."""
+    minibatch updates), fp32 ("highest", train.py:93-94), per rank `n` envs; gradients all-reduced when world > 1. The batch size grows
+    with the world (256 per rank: the reference's 256 at 4096 envs, 2048 at 8 x 4096), so every rank keeps the reference's per-GPU work
+    - 2 unrolls and 5120-transition minibatches - and the record is the weak-scaling series of the training step."""
     from phase_guided_terrain_traversal_b200 import ppo
-    pc = ppo.PPOConfig(num_envs=n, matmul_precision="highest")
+    pc = ppo.PPOConfig(num_envs=n * world, batch_size=256 * world, matmul_precision="highest")
     env, wenv, state = make_env(None, cfg, local_rank, n, rank * n, "stairs", table, 1, seed=5)
     tr = ppo.PPOTrainer(wenv, state, pc)
     for _ in range(2):
@@ -324,14 +326,15 @@ def train_step_record(torch, dev, cfg, local_rank, rank, world, table, barrier, 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     reps = 3
+    steps0 = tr.env_steps
     e0.record(torch.cuda.current_stream(dev))
     for _ in range(reps):
         m = tr.training_step()
     e1.record(torch.cuda.current_stream(dev))
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / reps
-    env_steps = pc.batch_size * pc.num_minibatches * pc.unroll_length * world
-    rec = {"value": env_steps / (ms * 1e-3), "unit": UNIT, "ms_per_training_step": ms, "env_steps_per_training_step": env_steps, "num_envs_per_gpu": n,
+    env_steps = (tr.env_steps - steps0) // reps              # the trainer's own count: unrolls x unroll_length x envs of all ranks
+    rec = {"value": env_steps / (ms * 1e-3), "unit": UNIT, "ms_per_training_step": ms, "env_steps_per_training_step": env_steps, "num_envs_per_gpu": n, "batch_size": pc.batch_size, "unrolls_per_training_step": tr.unrolls_per_step,
            "precision": "fp32 (matmul_precision highest, as training/train.py:93-94)", "learner": getattr(tr, "learner_kind", "torch autograd over library GEMMs + hand-written GAE / loss-head / clip+Adam kernels"),
            "total_loss": float(m["total_loss"])}
     env.close()
