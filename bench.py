@@ -205,9 +205,11 @@ def run_reference(args, cfg, table, rank):
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": workload_config(args, n, 1),
+        # the product arm's configuration (same flags -> same dict); what this arm actually stepped is `cpu_baseline.sample`
+        "config": workload_config(args, args.num_envs, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"each step = {n} envs (bounded sample of the {args.num_envs}-env workload), fp32 C restatement of the MJX step, OpenMP over envs"},
+                         "sample": f"each step = {n} envs on this host's {cores} threads (bounded sample of the {args.num_envs} envs/GPU x {args.gpus} GPU workload; the CPU rate does not "
+                                   f"depend on the env count beyond one env per thread), fp32 C restatement of the MJX step, OpenMP over envs"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference MJX/JAX stack not installable (no jax/mujoco wheels, no network): this is the restated CPU oracle, not MJX",
     }
