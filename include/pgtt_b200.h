@@ -210,6 +210,11 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* policy, int T, uint64_t seed, uint6
 int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B,
              float lambda, float gamma, float reward_scaling, float* vs, float* adv, void* stream);
 
+/* pgtt_gae plus what ppo_loss normalises the advantages with: moments [2] (DEVICE) = population mean and standard deviation of
+ * adv over the T x B minibatch, from the same launch (one block; B <= 1024 segments). */
+int pgtt_gae_moments(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
+                     float reward_scaling, float* vs, float* adv, float* moments, void* stream);
+
 /* Fused PPO loss head (brax ppo losses: NormalTanh log-prob of the stored raw action, importance ratio, clipped surrogate,
  * 0.25 MSE value loss, one-sample entropy estimate) for M = T * B transitions with A action dims, forward AND the
  * gradients with respect to the logits [M][2A] and the value predictions [M] in one launch. adv_moments: DEVICE float[2] =

@@ -746,30 +746,66 @@ int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint
 
 int64_t pgtt_policy_launch_count(pgtt_policy* p) { return p ? p->launches : 0; }
 
-// brax compute_gae: backward recursion over one trajectory segment per thread (coalesced across segments)
+// brax compute_gae: backward recursion over one trajectory segment per thread (coalesced across segments). `mom` (may be null;
+// needs the whole batch in ONE block): population mean and standard deviation of the advantages, two-pass (mean, then squared
+// deviations), every partial sum in a fixed order - what ppo_loss normalises the advantages with.
 __global__ void pgtt_gae_kernel(const float* __restrict__ trunc, const float* __restrict__ disc, const float* __restrict__ rew,
                                 const float* __restrict__ val, int T, int B, float lam, float gamma, float rscale,
-                                float* __restrict__ vs, float* __restrict__ adv) {
+                                float* __restrict__ vs, float* __restrict__ adv, float* __restrict__ mom) {
+  __shared__ float red[33];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float acc = 0.f, vs_next = val[(size_t)T * B + b];
-  for (int t = T - 1; t >= 0; t--) {
-    const size_t i = (size_t)t * B + b;
-    const float tr = trunc[i], mask = 1.f - tr, term = (1.f - disc[i]) * mask, r = rew[i] * rscale, v = val[i];
-    const float cont = gamma * (1.f - term);
-    const float delta = (r + cont * val[i + B] - v) * mask;
-    acc = delta + cont * mask * lam * acc;
-    const float vst = acc + v;
-    adv[i] = (r + cont * vs_next - v) * mask;
-    vs[i] = vst;
-    vs_next = vst;
+  float asum = 0.f;
+  if (b < B) {
+    float acc = 0.f, vs_next = val[(size_t)T * B + b];
+    for (int t = T - 1; t >= 0; t--) {
+      const size_t i = (size_t)t * B + b;
+      const float tr = trunc[i], mask = 1.f - tr, term = (1.f - disc[i]) * mask, r = rew[i] * rscale, v = val[i];
+      const float cont = gamma * (1.f - term);
+      const float delta = (r + cont * val[i + B] - v) * mask;
+      acc = delta + cont * mask * lam * acc;
+      const float vst = acc + v;
+      const float a = (r + cont * vs_next - v) * mask;
+      adv[i] = a;
+      asum += a;
+      vs[i] = vst;
+      vs_next = vst;
+    }
   }
+  if (!mom) return;                                          // (uniform)
+  auto block_sum = [&](float v) -> float {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();                                         // red[] of the previous call has been read
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float w = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+      if (threadIdx.x == 0) red[32] = w;
+    }
+    __syncthreads();
+    return red[32];
+  };
+  const float n = (float)T * (float)B;
+  const float mean = block_sum(asum) / n;
+  float dev = 0.f;
+  if (b < B) for (int t = 0; t < T; t++) { const float d = adv[(size_t)t * B + b] - mean; dev += d * d; }   // (own writes: visible to this thread)
+  const float var = block_sum(dev) / n;
+  if (threadIdx.x == 0) { mom[0] = mean; mom[1] = sqrtf(var); }
 }
 
 int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
              float reward_scaling, float* vs, float* adv, void* stream) {
   if (!truncation || !discount || !reward || !values || !vs || !adv || T <= 0 || B <= 0) return pfail(PGTT_ERR_ARG, "pgtt_gae: null argument or empty shape");
-  pgtt_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv);
+  pgtt_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, nullptr);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
+int pgtt_gae_moments(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
+                     float reward_scaling, float* vs, float* adv, float* moments, void* stream) {
+  if (!truncation || !discount || !reward || !values || !vs || !adv || !moments || T <= 0 || B <= 0) return pfail(PGTT_ERR_ARG, "pgtt_gae_moments: null argument or empty shape");
+  if (B > 1024) return pfail(PGTT_ERR_ARG, "pgtt_gae_moments: more than 1024 segments per minibatch (use pgtt_gae and reduce separately)");
+  pgtt_gae_kernel<<<1, (B + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, moments);
   PCUDA(cudaGetLastError());
   return PGTT_OK;
 }

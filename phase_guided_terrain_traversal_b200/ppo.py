@@ -58,6 +58,8 @@ class PPOConfig:                      # names and defaults of training/train.py:
     # accuracy, one autograd node per network); "layers": the per-layer tcgen05 GEMMs of csrc/pgtt_learner.cu; False = torch GEMMs
     # (CPU tests, comparisons)
     native_mlp: object = True
+    # the SGD step as a fixed sequence of this repo's kernels over static buffers, no autograd (needs native_mlp = True, fused_head, native_optimizer)
+    native_step: bool = True
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -583,6 +585,7 @@ class PPOTrainer:
         self._side = None
         self._aux = None
         self._data: Dict = {}
+        self._nb = None
         self.metrics: Dict = {}
         self.learner_kind = {
             True: "hand-written whole-MLP forward / backward on blocked split-bf16 tcgen05 GEMMs (fp32 accumulation, minibatch gather + normalisation fused into "
@@ -646,6 +649,84 @@ class PPOTrainer:
     def _fused_input(self) -> bool:
         return self.cfg.native_mlp is True
 
+    # -- the SGD step without autograd: every launch is one of this repo's kernels (plus three gathers) -------------------------------
+    def _native_step_ok(self) -> bool:
+        c = self.cfg
+        return bool(c.native_mlp is True and c.fused_head and c.native_step and self.flat_opt is not None and c.normalize_advantage and self.mb <= 1024)
+
+    def _sgd_body_native(self):
+        """One SGD step as a fixed launch sequence over static buffers (what brax's `sgd_step` / `loss_and_pgrad` / `optimizer.update` do,
+        training/train.py:135-161): minibatch index -> three gathers (raw actions, the four per-transition scalars, entropy noise) -> both
+        MLP forwards with the observation gather + normalisation fused in (`pgtt_mlp_forward_gather`; value network on a second stream) ->
+        `pgtt_gae_moments` -> `pgtt_ppo_head` (loss terms + gradients wrt logits / values) -> both MLP backwards (`pgtt_mlp_backward`, writing
+        straight into one flat gradient vector) -> [NCCL all-reduce] -> `pgtt_adam_clip`. Equals the autograd path (`_sgd_body`) to rounding
+        (tests/test_ppo.py::test_native_sgd_step_equals_the_autograd_step)."""
+        import ctypes as C
+        from . import _native as nat
+        torch, cfg, lib, dev = self.torch, self.cfg, nat.load_library(), self.dev
+        T, mb = cfg.unroll_length, self.mb
+        nobs, npriv = self.abi.nobs, self.abi.npriv
+        if self._nb is None:
+            f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+            flat_g = torch.zeros_like(self.flat_opt.flat)
+            views, off = [], 0
+            for p_ in self.params:
+                views.append(flat_g[off:off + p_.numel()].view_as(p_))
+                off += p_.numel()
+            L = len(self.policy_params[0])
+            mk = lambda ks, rows: _MlpHandle(lib, (ks[0].shape[0], *[k.shape[1] for k in ks]), rows, dev.index)
+            self._nb = {"logits": f(T * mb, 24), "base_all": f((T + 1) * mb), "vs": f(T, mb), "adv": f(T, mb), "mom": f(2), "g_logits": f(T * mb, 24),
+                        "g_base_all": torch.zeros((T + 1) * mb, dtype=torch.float32, device=dev), "sums": f(4), "flat_g": flat_g,
+                        "g_pol": (views[:L], views[L:2 * L]), "g_val": (views[2 * L:3 * L], views[3 * L:]),
+                        "h_pol": mk(self.policy_params[0], T * mb), "h_val": mk(self.value_params[0], (T + 1) * mb)}
+            if self._side is None:
+                self._side = torch.cuda.Stream(dev)
+        nb = self._nb
+        ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+        def chk(rc, err):
+            if rc:
+                raise nat.PgttError(rc, err().decode())
+        cur, side = torch.cuda.current_stream(dev), self._side
+        st = lambda s: C.c_void_p(s.cuda_stream)
+        idx = self._perm.index_select(0, self._mbi).reshape(-1)                          # [mb] segment ids of this minibatch
+        raw = self._data["raw_action"].index_select(1, idx)
+        scal = self._scal.index_select(2, idx)                                           # log_prob, reward, discount, truncation: [4, T, mb]
+        eps = self._eps.index_select(0, self._mbi)[0]
+        S = self._data["obs"].shape[1]
+        (m_o, i_o), (m_p, i_p) = self._norm_dev
+        dp = lambda t: t.data_ptr() if t is not None else None
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            chk(lib.pgtt_mlp_forward_gather(nb["h_val"].h, self._data["obs_priv"].data_ptr(), self._data["obs_priv"].shape[2], S, idx.data_ptr(), mb, dp(m_p), dp(i_p),
+                                            ptrs(self.value_params[0]), ptrs(self.value_params[1]), nb["base_all"].data_ptr(), st(side)), lib.pgtt_mlp_last_error)
+        chk(lib.pgtt_mlp_forward_gather(nb["h_pol"].h, self._data["obs"].data_ptr(), self._data["obs"].shape[2], S, idx.data_ptr(), mb, dp(m_o), dp(i_o),
+                                        ptrs(self.policy_params[0]), ptrs(self.policy_params[1]), nb["logits"].data_ptr(), st(cur)), lib.pgtt_mlp_last_error)
+        cur.wait_stream(side)
+        gae_args = (scal[3].data_ptr(), scal[2].data_ptr(), scal[1].data_ptr(), nb["base_all"].data_ptr(), T, mb, cfg.gae_lambda, cfg.discounting, cfg.reward_scaling,
+                    nb["vs"].data_ptr(), nb["adv"].data_ptr())
+        if cfg.global_advantage_norm and self.world > 1:
+            chk(lib.pgtt_gae(*gae_args, st(cur)), lib.pgtt_policy_last_error)
+            nb["mom"].copy_(torch.stack(self._moments(nb["adv"])).to(torch.float32))
+        else:
+            chk(lib.pgtt_gae_moments(*gae_args, nb["mom"].data_ptr(), st(cur)), lib.pgtt_policy_last_error)
+        chk(lib.pgtt_ppo_head(nb["logits"].data_ptr(), nb["base_all"].data_ptr(), raw.data_ptr(), scal[0].data_ptr(), nb["adv"].data_ptr(), nb["vs"].data_ptr(), eps.data_ptr(),
+                              nb["mom"].data_ptr(), T * mb, 12, cfg.clipping_epsilon, cfg.entropy_cost, 0.001, nb["g_logits"].data_ptr(), nb["g_base_all"].data_ptr(),
+                              nb["sums"].data_ptr(), st(cur)), lib.pgtt_policy_last_error)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):      # (the bootstrap row of g_base_all stays zero: no gradient flows through the bootstrap value)
+            chk(lib.pgtt_mlp_backward(nb["h_val"].h, nb["g_base_all"].data_ptr(), ptrs(nb["g_val"][0]), ptrs(nb["g_val"][1]), st(side)), lib.pgtt_mlp_last_error)
+        chk(lib.pgtt_mlp_backward(nb["h_pol"].h, nb["g_logits"].data_ptr(), ptrs(nb["g_pol"][0]), ptrs(nb["g_pol"][1]), st(cur)), lib.pgtt_mlp_last_error)
+        cur.wait_stream(side)
+        for t_ in (raw, scal, eps, idx):
+            t_.record_stream(side)
+        flat = nb["flat_g"]
+        if self.world > 1:
+            torch.distributed.all_reduce(flat, group=self.group)
+        self.flat_opt.step(flat, cfg.max_grad_norm, 1.0 / self.world)
+        sums = nb["sums"]
+        return {"total_loss": sums[0], "policy_loss": sums[1], "v_loss": sums[2], "entropy": sums[3]}
+
     def _minibatch(self):
         """Minibatch `self._mbi` of the current epoch, gathered ON THE DEVICE from the static full-data buffers: the index
         tensors are the only thing the host touches per SGD step, so the whole step (gather, forward, loss, backward,
@@ -678,14 +759,15 @@ class PPOTrainer:
         # captures and replays the same sequence (2.8x on 2 GPUs against issuing the step eagerly); PGTT_GRAPH_NCCL=0 opts out
         import os
         graphable = self.cfg.use_cuda_graph and (self.world == 1 or os.environ.get("PGTT_GRAPH_NCCL", "1") == "1")
+        body = self._sgd_body_native if self._native_step_ok() else (lambda: self._sgd_body(self._minibatch()))
         if not graphable:
-            return self._sgd_body(self._minibatch())
+            return body()
         if self._graph is None:
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
-                for _ in range(3):                                   # warm-up outside capture (allocator, Adam state)
-                    self._sgd_body(self._minibatch())
+                for _ in range(3):                                   # warm-up outside capture (allocator, Adam state, MLP handles)
+                    body()
             torch.cuda.current_stream(self.dev).wait_stream(s)
             # no garbage collection while capturing: a collected env / policy handle would run pgtt_*_destroy
             # (cudaDeviceSynchronize + cudaFree), which is illegal inside a capture
@@ -696,7 +778,7 @@ class PPOTrainer:
             try:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
-                    self._static_metrics = self._sgd_body(self._minibatch())
+                    self._static_metrics = body()
             finally:
                 gc.enable()
             # the warm-up steps changed the parameters: acceptable for training (three extra SGD steps on the first

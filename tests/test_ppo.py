@@ -446,3 +446,43 @@ def test_in_training_evaluation_reports_the_keys_progress_reads(train_cfg):
     assert "training/reward_per_step" in got[-1][1] and "training/reward_per_step" not in got[0][1]
     a, b = out[True][1], out[False][1]
     assert a["env_steps"] == b["env_steps"] and abs(a["reward_per_step"] - b["reward_per_step"]) < 1e-6 and abs(a["total_loss"] - b["total_loss"]) < 1e-4, (a, b)
+
+
+@pytest.mark.gpu
+def test_native_sgd_step_equals_the_autograd_step(train_cfg):
+    """The product SGD step (`PPOTrainer._sgd_body_native`: gathers -> pgtt_mlp_forward_gather x 2 -> pgtt_gae_moments -> pgtt_ppo_head ->
+    pgtt_mlp_backward x 2 -> pgtt_adam_clip, no autograd) against the autograd statement of the same step (`_sgd_body` over `ppo_loss`) on the
+    same minibatch from the same parameter / optimiser state: loss terms to 1e-5, the flat gradient to 1e-4 of its largest entry, the
+    parameters after the Adam step to 2 lr (Adam's first steps are sign-like: an entry whose gradient is ~0 may step the other way)."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo, prng
+    from phase_guided_terrain_traversal_b200.go2.joystick_pgtt import Joystick
+    from phase_guided_terrain_traversal_b200.go2.randomize_simple import domain_randomize
+    from phase_guided_terrain_traversal_b200.wrapper import wrap_for_brax_training
+    n = 256
+    cfg = ppo.PPOConfig(num_envs=n, batch_size=64, num_minibatches=8, num_updates_per_batch=1, use_cuda_graph=False, seed=9)
+    env = Joystick(task="flat_terrain", config=train_cfg)
+    keys = prng.env_keys(4, n)
+    wenv = wrap_for_brax_training(env, episode_length=1000, randomization_fn=lambda m: domain_randomize(m, rng=keys))
+    tr = ppo.PPOTrainer(wenv, wenv.reset(keys), cfg)
+    assert tr._native_step_ok()
+    tr.training_step()                                   # fills the transition store, the normaliser statistics, the permutation, the noise
+    opt = tr.flat_opt
+    saved = [t.clone() for t in (opt.flat, opt.m, opt.v, opt.t)]
+    tr._mbi.fill_(3)
+    # autograd statement
+    m_auto = {k: float(v) for k, v in tr._sgd_body(tr._minibatch()).items()}
+    g_auto = torch.cat([p.grad.reshape(-1) for p in tr.params]).clone()
+    p_auto = opt.flat.clone()
+    for dst, src in zip((opt.flat, opt.m, opt.v, opt.t), saved):
+        dst.copy_(src)
+    # product path
+    m_nat = {k: float(v) for k, v in tr._sgd_body_native().items()}
+    torch.cuda.synchronize()
+    g_nat, p_nat = tr._nb["flat_g"], opt.flat
+    for k in m_auto:
+        assert abs(m_nat[k] - m_auto[k]) <= 1e-5 * max(1.0, abs(m_auto[k])), (k, m_nat[k], m_auto[k])
+    assert float((g_nat - g_auto).abs().max()) <= 1e-4 * float(g_auto.abs().max()), (float((g_nat - g_auto).abs().max()), float(g_auto.abs().max()))
+    assert float(g_auto.abs().max()) > 0
+    assert float((p_nat - p_auto).abs().max()) <= 2.0 * cfg.learning_rate + 1e-7
+    assert float((p_nat - p_auto).abs().mean()) <= 0.02 * cfg.learning_rate
