@@ -210,6 +210,12 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* policy, int T, uint64_t seed, uint6
 int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B,
              float lambda, float gamma, float reward_scaling, float* vs, float* adv, void* stream);
 
+/* Everything of minibatch number *mbi that is not an observation, in one launch (all DEVICE): idx [mb] = perm[*mbi][:] (int64 segment ids, also what
+ * pgtt_mlp_forward_gather takes), raw [T][mb][A] from raw_all [T][S][A], scal [n_scal][T][mb] from scal_all [n_scal][T][S], eps [T][mb][A] = eps_all[*mbi]
+ * (brax `sgd_step`: shuffle, reshape into minibatches, slice; training/train.py:135-161). *mbi is read on the device, so a captured graph serves every minibatch. */
+int pgtt_minibatch_gather(const long long* perm, const long long* mbi, int mb, int S, int T, int A, int n_scal, const float* raw_all, const float* scal_all,
+                          const float* eps_all, long long* idx, float* raw, float* scal, float* eps, void* stream);
+
 /* pgtt_gae plus what ppo_loss normalises the advantages with: moments [2] (DEVICE) = population mean and standard deviation of
  * adv over the T x B minibatch, from the same launch (one block; B <= 1024 segments). */
 int pgtt_gae_moments(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,

@@ -810,6 +810,42 @@ int pgtt_gae_moments(const float* truncation, const float* discount, const float
   return PGTT_OK;
 }
 
+// Everything of a minibatch that is not an observation, in one launch: segment ids idx[j] = perm[mbi][j], then for t < T, j < mb
+// the raw actions [T][S][A] -> [T][mb][A], the n_scal per-transition scalars [n_scal][T][S] -> [n_scal][T][mb] and the entropy noise
+// of minibatch mbi, eps_all[mbi] ([T][mb][A], copied). (brax sgd_step's `convert_data` + minibatch slicing, training/train.py:135-161.)
+__global__ void pgtt_minibatch_gather_kernel(const long long* __restrict__ perm, const long long* __restrict__ mbi, int mb, int S, int T, int A, int n_scal,
+                                             const float* __restrict__ raw_all, const float* __restrict__ scal_all, const float* __restrict__ eps_all,
+                                             long long* __restrict__ idx, float* __restrict__ raw, float* __restrict__ scal, float* __restrict__ eps) {
+  const long long m = *mbi;
+  const long long* pm = perm + m * mb;
+  const long long n_raw = (long long)T * mb * A, n_sc = (long long)n_scal * T * mb;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_raw + n_sc + mb; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_raw) {
+      const int a = (int)(i % A); const long long tj = i / A; const int j = (int)(tj % mb); const long long t = tj / mb;
+      raw[i] = raw_all[(t * S + pm[j]) * A + a];
+    } else if (i < 2 * n_raw) {
+      eps[i - n_raw] = eps_all[m * n_raw + (i - n_raw)];
+    } else if (i < 2 * n_raw + n_sc) {
+      const long long k = i - 2 * n_raw; const int j = (int)(k % mb); const long long ct = k / mb;     // ct = c * T + t
+      scal[k] = scal_all[ct * S + pm[j]];
+    } else {
+      const long long j = i - 2 * n_raw - n_sc;
+      idx[j] = pm[j];
+    }
+  }
+}
+
+int pgtt_minibatch_gather(const long long* perm, const long long* mbi, int mb, int S, int T, int A, int n_scal, const float* raw_all, const float* scal_all,
+                          const float* eps_all, long long* idx, float* raw, float* scal, float* eps, void* stream) {
+  if (!perm || !mbi || !raw_all || !scal_all || !eps_all || !idx || !raw || !scal || !eps || mb < 1 || S < 1 || T < 1 || A < 1 || n_scal < 1)
+    return pfail(PGTT_ERR_ARG, "pgtt_minibatch_gather: null argument or empty shape");
+  const long long n = 2LL * T * mb * A + (long long)n_scal * T * mb + mb;
+  pgtt_minibatch_gather_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, (cudaStream_t)stream>>>(perm, mbi, mb, S, T, A, n_scal, raw_all, scal_all, eps_all,
+                                                                                                                      idx, raw, scal, eps);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
 // Fused PPO head: one thread per transition; forward terms and gradients (see include/pgtt_b200.h)
 #define HEAD_MAXA 16
 __global__ void pgtt_ppo_head_kernel(const float* __restrict__ logits, const float* __restrict__ baseline, const float* __restrict__ raw,

@@ -649,14 +649,14 @@ class PPOTrainer:
     def _fused_input(self) -> bool:
         return self.cfg.native_mlp is True
 
-    # -- the SGD step without autograd: every launch is one of this repo's kernels (plus three gathers) -------------------------------
+    # -- the SGD step without autograd: every launch is one of this repo's kernels ------------------------------------------------------
     def _native_step_ok(self) -> bool:
         c = self.cfg
         return bool(c.native_mlp is True and c.fused_head and c.native_step and self.flat_opt is not None and c.normalize_advantage and self.mb <= 1024)
 
     def _sgd_body_native(self):
         """One SGD step as a fixed launch sequence over static buffers (what brax's `sgd_step` / `loss_and_pgrad` / `optimizer.update` do,
-        training/train.py:135-161): minibatch index -> three gathers (raw actions, the four per-transition scalars, entropy noise) -> both
+        training/train.py:135-161): minibatch index -> `pgtt_minibatch_gather` (segment ids, raw actions, the four per-transition scalars, entropy noise: one launch) -> both
         MLP forwards with the observation gather + normalisation fused in (`pgtt_mlp_forward_gather`; value network on a second stream) ->
         `pgtt_gae_moments` -> `pgtt_ppo_head` (loss terms + gradients wrt logits / values) -> both MLP backwards (`pgtt_mlp_backward`, writing
         straight into one flat gradient vector) -> [NCCL all-reduce] -> `pgtt_adam_clip`. Equals the autograd path (`_sgd_body`) to rounding
@@ -678,7 +678,8 @@ class PPOTrainer:
             self._nb = {"logits": f(T * mb, 24), "base_all": f((T + 1) * mb), "vs": f(T, mb), "adv": f(T, mb), "mom": f(2), "g_logits": f(T * mb, 24),
                         "g_base_all": torch.zeros((T + 1) * mb, dtype=torch.float32, device=dev), "sums": f(4), "flat_g": flat_g,
                         "g_pol": (views[:L], views[L:2 * L]), "g_val": (views[2 * L:3 * L], views[3 * L:]),
-                        "h_pol": mk(self.policy_params[0], T * mb), "h_val": mk(self.value_params[0], (T + 1) * mb)}
+                        "h_pol": mk(self.policy_params[0], T * mb), "h_val": mk(self.value_params[0], (T + 1) * mb),
+                        "idx": torch.zeros(mb, dtype=torch.int64, device=dev), "raw": f(T, mb, 12), "scal": f(len(_SCALARS), T, mb), "eps": f(T, mb, 12)}
             if self._side is None:
                 self._side = torch.cuda.Stream(dev)
         nb = self._nb
@@ -689,11 +690,10 @@ class PPOTrainer:
                 raise nat.PgttError(rc, err().decode())
         cur, side = torch.cuda.current_stream(dev), self._side
         st = lambda s: C.c_void_p(s.cuda_stream)
-        idx = self._perm.index_select(0, self._mbi).reshape(-1)                          # [mb] segment ids of this minibatch
-        raw = self._data["raw_action"].index_select(1, idx)
-        scal = self._scal.index_select(2, idx)                                           # log_prob, reward, discount, truncation: [4, T, mb]
-        eps = self._eps.index_select(0, self._mbi)[0]
         S = self._data["obs"].shape[1]
+        idx, raw, scal, eps = nb["idx"], nb["raw"], nb["scal"], nb["eps"]                 # segment ids [mb]; [T, mb, 12]; log_prob, reward, discount, truncation [4, T, mb]; [T, mb, 12]
+        chk(lib.pgtt_minibatch_gather(self._perm.data_ptr(), self._mbi.data_ptr(), mb, S, T, 12, len(_SCALARS), self._data["raw_action"].data_ptr(), self._scal.data_ptr(),
+                                      self._eps.data_ptr(), idx.data_ptr(), raw.data_ptr(), scal.data_ptr(), eps.data_ptr(), st(cur)), lib.pgtt_policy_last_error)
         (m_o, i_o), (m_p, i_p) = self._norm_dev
         dp = lambda t: t.data_ptr() if t is not None else None
         side.wait_stream(cur)
@@ -718,8 +718,6 @@ class PPOTrainer:
             chk(lib.pgtt_mlp_backward(nb["h_val"].h, nb["g_base_all"].data_ptr(), ptrs(nb["g_val"][0]), ptrs(nb["g_val"][1]), st(side)), lib.pgtt_mlp_last_error)
         chk(lib.pgtt_mlp_backward(nb["h_pol"].h, nb["g_logits"].data_ptr(), ptrs(nb["g_pol"][0]), ptrs(nb["g_pol"][1]), st(cur)), lib.pgtt_mlp_last_error)
         cur.wait_stream(side)
-        for t_ in (raw, scal, eps, idx):
-            t_.record_stream(side)
         flat = nb["flat_g"]
         if self.world > 1:
             torch.distributed.all_reduce(flat, group=self.group)
