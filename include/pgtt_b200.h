@@ -176,6 +176,8 @@ int pgtt_policy_destroy(pgtt_policy* p);
 /* kernels[l]: HOST float [in][out] row-major (flax `kernel`), biases[l]: HOST float [out];
  * obs_mean / obs_std: HOST float [obs_dim] (brax running statistics) or NULL for identity. */
 int pgtt_policy_set_params(pgtt_policy* p, const float* const* kernels, const float* const* biases, const float* obs_mean, const float* obs_std);
+/* the same from DEVICE fp32 arrays, packed by a kernel on `stream` (no host copy, no synchronisation): the learner -> collector hand-over */
+int pgtt_policy_set_params_device(pgtt_policy* p, const float* const* kernels, const float* const* biases, const float* obs_mean, const float* obs_std, void* stream);
 /* obs DEVICE [n][obs_dim]. eps DEVICE [n][act_dim] or NULL (internal counter-based N(0,1) keyed by seed, step).
  * Outputs DEVICE: action [n][act_dim] = tanh(raw); raw_action [n][act_dim], log_prob [n], logits [n][2 act_dim] may be NULL. */
 int pgtt_policy_act(pgtt_policy* p, const float* obs, int n, uint64_t seed, uint64_t step, int deterministic, const float* eps,

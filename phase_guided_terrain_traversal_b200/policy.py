@@ -67,6 +67,22 @@ class PolicyNet:
                                                          std.ctypes.data if std is not None else None))
         self.params = (ks, bs, mean, std)
 
+    def set_params_device(self, kernels, biases, obs_mean=None, obs_std=None):
+        """The same from CUDA float32 tensors on this handle's device, packed by a kernel on the current stream: no host copies, no
+        synchronisation (`pgtt_policy_set_params_device`). `self.params` (the host copy `set_params` keeps) is dropped."""
+        torch = self.torch
+        n = len(self.sizes) - 1
+        ts = list(kernels) + list(biases) + [t for t in (obs_mean, obs_std) if t is not None]
+        assert len(kernels) == n and len(biases) == n and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+        for l in range(n):
+            assert tuple(kernels[l].shape) == (self.sizes[l], self.sizes[l + 1]) and tuple(biases[l].shape) == (self.sizes[l + 1],)
+        kp = (C.c_void_p * n)(*[k.data_ptr() for k in kernels])
+        bp = (C.c_void_p * n)(*[b.data_ptr() for b in biases])
+        stream = C.c_void_p(torch.cuda.current_stream(kernels[0].device).cuda_stream)
+        check(self.lib, self.lib.pgtt_policy_set_params_device(self.h, kp, bp, obs_mean.data_ptr() if obs_mean is not None else None,
+                                                                obs_std.data_ptr() if obs_std is not None else None, stream))
+        self.params = None
+
     def init_random(self, seed: int = 0):
         """Random-init weights of this architecture (lecun-uniform like flax Dense), identity normaliser."""
         g = np.random.default_rng(seed)

@@ -585,6 +585,7 @@ class PPOTrainer:
         self._side = None
         self._aux = None
         self._data: Dict = {}
+        self._norm_seen = False             # host-side: the running statistics hold at least one batch
         self._nb = None
         self.metrics: Dict = {}
         self.learner_kind = {
@@ -596,11 +597,12 @@ class PPOTrainer:
 
     # -- policy kernel <- learner parameters ---------------------------------------------------------------------------------
     def _sync_policy(self):
-        ks, bs = self.policy_params
-        if self.cfg.normalize_observations and float(self.norm_state.count) > 0:
-            self.net.set_params(ks, bs, self.norm_state.mean.float(), self.norm_state.std.float())
+        """Stream-ordered, on the device: a packing kernel reads the fp32 parameters and the running statistics (no host copy, no sync)."""
+        ks, bs = [k.detach() for k in self.policy_params[0]], [b.detach() for b in self.policy_params[1]]
+        if self.cfg.normalize_observations and self._norm_seen:
+            self.net.set_params_device(ks, bs, self.norm_state.mean.float(), self.norm_state.std.float())
         else:
-            self.net.set_params(ks, bs)
+            self.net.set_params_device(ks, bs)
 
     # -- one SGD step (optionally replayed from a CUDA graph) ----------------------------------------------------------------
     def _moments(self, adv):
@@ -815,6 +817,7 @@ class PPOTrainer:
             obs, priv = data["obs"][..., :self.abi.nobs], data["obs_priv"][..., :self.abi.npriv]
             self.norm_state.update(obs[:T], self.group)
             self.norm_priv.update(priv[:T], self.group)
+            self._norm_seen = True
             if self._fused_input():     # raw observations stay in the store; the statistics travel to the input kernel (static buffers: graph replays see them)
                 for (m32, i32), rs in zip(self._norm_dev, (self.norm_state, self.norm_priv)):
                     m32.copy_(rs.mean)
@@ -868,6 +871,7 @@ class PPOTrainer:
             rs.mean = torch.as_tensor(mean, dtype=torch.float64, device=self.dev)
             rs.std = torch.as_tensor(std, dtype=torch.float64, device=self.dev)
             rs.summed_var = rs.std * rs.std * cnt
+            self._norm_seen = True
         self._sync_policy()
 
 

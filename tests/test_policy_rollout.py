@@ -214,3 +214,32 @@ def test_evaluator_closed_loop_with_a_reference_policy(train_cfg):
     assert abs(m[5] - g["mean"][5]) < 0.05                                    # gravity z
     assert abs(s[30] - g["std"][30]) < 0.02 and abs(m[155] - g["mean"][155]) < 0.1
     assert 0.5 < s[6:18].mean() / g["std"][6:18].mean() < 2.0
+
+
+@pytest.mark.gpu
+def test_device_side_parameter_hand_over_equals_the_host_one():
+    """`pgtt_policy_set_params_device` (packing kernel reading CUDA fp32 tensors, stream-ordered) against `pgtt_policy_set_params` (host repack):
+    the two handles produce bit-identical actions, log-probs and logits for the same observations, seed and step."""
+    import torch
+    from phase_guided_terrain_traversal_b200.policy import PolicyNet
+    g = np.random.default_rng(5)
+    sizes = (171, 512, 256, 128, 24)
+    ks = [(g.uniform(-1, 1, (i, o)) * np.sqrt(3.0 / i)).astype(np.float32) for i, o in zip(sizes[:-1], sizes[1:])]
+    bs = [g.normal(0, 0.1, o).astype(np.float32) for o in sizes[1:]]
+    mean, std = g.normal(0, 1, 171).astype(np.float32), g.uniform(0.5, 2.0, 171).astype(np.float32)
+    obs = torch.from_numpy(g.normal(0, 1, (300, 171)).astype(np.float32)).cuda()
+    a, b = PolicyNet(sizes), PolicyNet(sizes)
+    a.set_params(ks, bs, mean, std)
+    tc = lambda x: torch.from_numpy(x).cuda()
+    b.set_params_device([tc(k) for k in ks], [tc(x) for x in bs], tc(mean), tc(std))
+    ra, rb = a.act(obs, seed=3, want_logits=True), b.act(obs, seed=3, want_logits=True)
+    torch.cuda.synchronize()
+    for k in ("action", "raw_action", "log_prob", "logits"):
+        assert torch.equal(ra[k], rb[k]), k
+    # a second hand-over overwrites every packed weight (nothing stale survives), identity normaliser included
+    half = [(k * 0.5).astype(np.float32) for k in ks]
+    b.set_params_device([tc(k) for k in half], [tc(x) for x in bs])
+    a.set_params(half, bs)
+    ra, rb = a.act(obs, seed=4, want_logits=True), b.act(obs, seed=4, want_logits=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ra["logits"], rb["logits"]) and torch.equal(ra["action"], rb["action"])
