@@ -996,7 +996,7 @@ DEV void linesearch(WS& w, Rows& R, const SolveState& S, int lane) {
     for (int t = 0; t < 2; t++) { C.m[t] = m; C.lm[t] = lm; C.s[t][0] = s0; C.s[t][1] = s1; C.s[t][2] = s2; }
   }
   const LSPoint p0 = ls_eval(0.f, R, q, lq, qg, C, lane);
-  const LSPoint l0 = ls_eval(p0.alpha - p0.d0 / p0.d1, R, q, lq, qg, C, lane);
+  const LSPoint l0 = ls_eval(p0.alpha - fdiv_(p0.d0, p0.d1), R, q, lq, qg, C, lane);
   const bool lesser = l0.d0 < p0.d0;
   LSPoint hi = lesser ? p0 : l0, lo = lesser ? l0 : p0;
   bool swap = true;
@@ -1008,8 +1008,8 @@ DEV void linesearch(WS& w, Rows& R, const SolveState& S, int lane) {
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (all_lanes(done)) break;
-    const LSPoint lo_next = ls_eval(lo.alpha - lo.d0 / lo.d1, R, q, lq, qg, C, lane);
-    const LSPoint hi_next = ls_eval(hi.alpha - hi.d0 / hi.d1, R, q, lq, qg, C, lane);
+    const LSPoint lo_next = ls_eval(lo.alpha - fdiv_(lo.d0, lo.d1), R, q, lq, qg, C, lane);
+    const LSPoint hi_next = ls_eval(hi.alpha - fdiv_(hi.d0, hi.d1), R, q, lq, qg, C, lane);
     const LSPoint mid = ls_eval(0.5f * (lo.alpha + hi.alpha), R, q, lq, qg, C, lane);
     const bool s_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (s_lo_next) lo = lo_next;
@@ -1066,9 +1066,9 @@ DEV int solve(WS& w, Rows& R, int lane) {
     float gn = 0.f;
     if (lane < NV) { const float gr = w.Ma[lane] - w.qs[lane] - w.qfc[lane]; w.grad[lane] = gr; gn = gr * gr; }
     if (niter > 0 && GC.iterations == 1) break;
-    const float improvement = (S.prev_cost - S.cost) / GC.solver_scale;
+    const float improvement = fdiv_(S.prev_cost - S.cost, GC.solver_scale);
     gn = warp_sum(gn);
-    const float gradient = sqrtf(gn) / GC.solver_scale;
+    const float gradient = fdiv_(sqrtf(gn), GC.solver_scale);
     bool done = niter >= GC.iterations;
     done |= improvement < GC.tolerance;
     done |= gradient < GC.tolerance;

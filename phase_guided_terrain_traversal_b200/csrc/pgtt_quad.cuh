@@ -937,7 +937,7 @@ DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, co
   {
     const float a0 = 0.f;
     q_ls_eval<1>(&p0, &a0, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);
-    const float a1 = p0.alpha - p0.d0 / p0.d1;
+    const float a1 = p0.alpha - fdiv_(p0.d0, p0.d1);
     q_ls_eval<1>(&l0, &a1, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);
   }
   const bool lesser = l0.d0 < p0.d0;
@@ -956,7 +956,7 @@ DEV void q_linesearch(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& Mm, co
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (GC.quad_ls_vote ? cta_all(done) : (round >= GC.ls_iterations)) break;
     QLSPoint pts[3];
-    const float al3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+    const float al3[3] = {lo.alpha - fdiv_(lo.d0, lo.d1), hi.alpha - fdiv_(hi.d0, hi.d1), 0.5f * (lo.alpha + hi.alpha)};
     q_ls_eval<3>(pts, al3, CP, CX, Lm, qP, qX, qL, qg, anyX, anyL);
     const QLSPoint lo_next = pts[0], hi_next = pts[1], mid = pts[2];
     if (!done) {
@@ -1041,8 +1041,8 @@ DEV int q_solve_constraints(QSol& S, QCon& CP, QCon& CX, QLim& Lm, const QMass& 
     for (int a = 0; a < 6; a++) { grad.b[a] = S.Ma.b[a] - qs.b[a] - S.qfc.b[a]; gnb += grad.b[a] * grad.b[a]; }
     const float gn = gnb + qsum(gnl);
     if (live) {
-      const float improvement = (S.prev - S.cost) / GC.solver_scale;
-      const float gradient = sqrtf(gn) / GC.solver_scale;
+      const float improvement = fdiv_(S.prev - S.cost, GC.solver_scale);
+      const float gradient = fdiv_(sqrtf(gn), GC.solver_scale);
       bool done = niter >= GC.iterations;
       if (GC.iterations == 1) done = niter > 0;
       else { done |= improvement < GC.tolerance; done |= gradient < GC.tolerance; }

@@ -55,6 +55,10 @@ DEV void sincos_(float a, float* s, float* c) {
   if (q & 2) { sn = -sn; cs = -cs; }
   *s = sn; *c = cs;
 }
+// approximate division (MUFU.RCP + multiply, 2 ulp) for the solver's scalar control quantities - Newton-step lengths of the line search,
+// convergence measures: they steer an iteration whose result is compared at 1e-3, and the IEEE sequence is ~8 instructions on a
+// latency-bound dependent chain (the host-emulated build divides exactly)
+DEV float fdiv_(float a, float b) { return __fdividef(a, b); }
 // un-contracted multiply-add: random draws must not depend on whether the compiler forms an FMA
 DEV float mul_add_nofma(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
 #endif

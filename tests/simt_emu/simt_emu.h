@@ -84,6 +84,7 @@ DEV float4 ldg4(const float4* p) { return *p; }
 DEV int popc(unsigned x) { return __builtin_popcount(x); }
 DEV int ffs_(unsigned x) { return __builtin_ffs((int)x); }
 DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+DEV float fdiv_(float a, float b) { return a / b; }
 DEV void sincos_(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
 DEV float mul_add_nofma(float a, float b, float c) { return a * b + c; }  // built with -ffp-contract=off
 DEV float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }

@@ -1,0 +1,3 @@
+set -x
+for i in 1 2; do python tools/kernel_times.py stairs 8192 level07 100 1 2>&1 | grep back; done
+timeout 900 python -m pytest tests/test_kernel_parity.py -m gpu -q -x 2>&1 | tail -4 | cut -c1-300
