@@ -212,6 +212,12 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* policy, int T, uint64_t seed, uint6
 int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B,
              float lambda, float gamma, float reward_scaling, float* vs, float* adv, void* stream);
 
+/* out [2][cols] (DEVICE double) = column sums and column sums of squares of x [rows][cols] (DEVICE fp32, row stride ld), accumulated in float64 in a fixed order:
+ * the batch statistics brax's running_statistics.update folds into the observation normaliser (training/train.py:140). scratch: DEVICE double
+ * [pgtt_col_moments_scratch_doubles(cols)]. Two launches on `stream`. */
+long long pgtt_col_moments_scratch_doubles(int cols);
+int pgtt_col_moments(const float* x, long long rows, int cols, int ld, double* out, double* scratch, void* stream);
+
 /* Everything of minibatch number *mbi that is not an observation, in one launch (all DEVICE): idx [mb] = perm[*mbi][:] (int64 segment ids, also what
  * pgtt_mlp_forward_gather takes), raw [T][mb][A] from raw_all [T][S][A], scal [n_scal][T][mb] from scal_all [n_scal][T][S], eps [T][mb][A] = eps_all[*mbi]
  * (brax `sgd_step`: shuffle, reshape into minibatches, slice; training/train.py:135-161). *mbi is read on the device, so a captured graph serves every minibatch. */

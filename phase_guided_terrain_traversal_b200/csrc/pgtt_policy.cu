@@ -859,6 +859,37 @@ int pgtt_gae_moments(const float* truncation, const float* discount, const float
   return PGTT_OK;
 }
 
+// Column sums and sums of squares of an fp32 matrix [rows][cols] (row stride ld) in float64 - what brax's running_statistics.update needs of a
+// batch of observations (training/train.py:140 normalize_observations=True). Two launches, fixed summation order (deterministic): per-block
+// partials over a strided share of the rows (one column per thread, coalesced along the row), then one thread per column adds the partials.
+#define CM_BLOCKS 592
+#define CM_THREADS 256
+__global__ void __launch_bounds__(CM_THREADS) pgtt_col_moments_kernel(const float* __restrict__ x, long long rows, int cols, int ld, double* __restrict__ part) {
+  for (int c = threadIdx.x; c < cols; c += CM_THREADS) {
+    double s = 0.0, q = 0.0;
+    for (long long r = blockIdx.x; r < rows; r += CM_BLOCKS) { const double v = (double)__ldg(x + r * ld + c); s += v; q += v * v; }
+    part[((size_t)blockIdx.x * 2) * cols + c] = s;
+    part[((size_t)blockIdx.x * 2 + 1) * cols + c] = q;
+  }
+}
+__global__ void pgtt_col_moments_sum_kernel(const double* __restrict__ part, int cols, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // i < 2 * cols: sums then sums of squares
+  if (i >= 2 * cols) return;
+  const int which = i / cols, c = i % cols;
+  double s = 0.0;
+  for (int b = 0; b < CM_BLOCKS; b++) s += part[((size_t)b * 2 + which) * cols + c];
+  out[i] = s;
+}
+long long pgtt_col_moments_scratch_doubles(int cols) { return (long long)CM_BLOCKS * 2 * cols; }
+int pgtt_col_moments(const float* x, long long rows, int cols, int ld, double* out, double* scratch, void* stream) {
+  if (!x || !out || !scratch || rows < 1 || cols < 1 || ld < cols) return pfail(PGTT_ERR_ARG, "pgtt_col_moments: bad argument");
+  pgtt_col_moments_kernel<<<CM_BLOCKS, CM_THREADS, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, scratch);
+  PCUDA(cudaGetLastError());
+  pgtt_col_moments_sum_kernel<<<(2 * cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, cols, out);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
 // Everything of a minibatch that is not an observation, in one launch: segment ids idx[j] = perm[mbi][j], then for t < T, j < mb
 // the raw actions [T][S][A] -> [T][mb][A], the n_scal per-transition scalars [n_scal][T][S] -> [n_scal][T][mb] and the entropy noise
 // of minibatch mbi, eps_all[mbi] ([T][mb][A], copied). (brax sgd_step's `convert_data` + minibatch slicing, training/train.py:135-161.)

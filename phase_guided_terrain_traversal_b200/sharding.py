@@ -40,12 +40,26 @@ def allreduce_moments(x, group=None):
     import torch
     import torch.distributed as dist
     feat = x.shape[1:]
-    xf = x.reshape(x.shape[0], -1).to(torch.float64)
-    # (torch.full, not torch.tensor: no host-to-device copy, so the reduction can sit inside a CUDA-graph capture)
-    packed = torch.cat([torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=x.device), xf.sum(0), (xf * xf).sum(0)])
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] * x.shape[1] >= 1 << 16:
+        # large fp32 matrices (the observation batches of the normaliser, possibly a column slice of a padded store): one pass of the hand-written
+        # float64 column-moment kernel instead of a float64 copy and two reductions
+        import ctypes as C
+        from . import _native as nat
+        lib = nat.load_library()
+        rows, cols = x.shape
+        sums = torch.empty(2 * cols, dtype=torch.float64, device=x.device)
+        scratch = torch.empty(int(lib.pgtt_col_moments_scratch_doubles(cols)), dtype=torch.float64, device=x.device)
+        rc = lib.pgtt_col_moments(x.data_ptr(), rows, cols, x.stride(0), sums.data_ptr(), scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        if rc:
+            raise nat.PgttError(rc, lib.pgtt_policy_last_error().decode())
+        packed = torch.cat([torch.full((1,), float(rows), dtype=torch.float64, device=x.device), sums])
+    else:
+        xf = x.reshape(x.shape[0], -1).to(torch.float64)
+        # (torch.full, not torch.tensor: no host-to-device copy, so the reduction can sit inside a CUDA-graph capture)
+        packed = torch.cat([torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=x.device), xf.sum(0), (xf * xf).sum(0)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    d = xf.shape[1]
+    d = (packed.numel() - 1) // 2
     count = packed[0]
     mean = packed[1:1 + d] / count
     var = (packed[1 + d:] / count - mean * mean).clamp_min(0.0)

@@ -486,3 +486,25 @@ def test_native_sgd_step_equals_the_autograd_step(train_cfg):
     assert float(g_auto.abs().max()) > 0
     assert float((p_nat - p_auto).abs().max()) <= 2.0 * cfg.learning_rate + 1e-7
     assert float((p_nat - p_auto).abs().mean()) <= 0.02 * cfg.learning_rate
+
+
+@pytest.mark.gpu
+def test_column_moment_kernel_matches_float64_statistics():
+    """`sharding.allreduce_moments` on a large CUDA fp32 matrix runs the hand-written float64 column-moment kernel (`pgtt_col_moments`); a
+    column slice of a padded store (row stride 172 for 171 columns) must give the float64 mean / variance of torch to 1e-12, and the
+    running statistics built from it must equal the ones built from the generic path."""
+    import torch
+    from phase_guided_terrain_traversal_b200 import ppo, sharding
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    store = torch.randn(21, 512, 172, device="cuda", generator=g) * 3.0 + 0.7
+    x = store[:20, :, :171].reshape(-1, 171)
+    assert x.data_ptr() == store.data_ptr() and x.stride(0) == 172                       # a view: nothing was copied
+    n, mean, var = sharding.allreduce_moments(x)
+    xd = x.double()
+    assert float(n) == x.shape[0]
+    assert float((mean - xd.mean(0)).abs().max()) < 1e-12 and float((var - xd.var(0, unbiased=False)).abs().max()) < 1e-10
+    a, b = ppo.RunningStats(171, x.device), ppo.RunningStats(171, x.device)
+    a.update(store[:20, :, :171])
+    b.update(store[:20, :, :171].cpu().to("cuda").contiguous()[:, :64])                  # small batches take the generic path ...
+    b.update(store[:20, :, :171].contiguous()[:, 64:])                                  # ... large ones the kernel: merged statistics agree
+    assert float((a.mean - b.mean).abs().max()) < 1e-12 and float((a.std - b.std).abs().max()) < 1e-10
