@@ -4,8 +4,8 @@
 Workload (N=1): BASELINE config[1] = `Joystick("stairs")` on terrains/level1.npy, 4096 envs, no
 dynamics DR (terrain assignment only), synthetic random joystick commands (env-internal
 `sample_command`) and U(-1,1) actions, episode wrapper + auto-reset on. One "step" = one wrapped
-`env.step` over all envs = two launches: the physics kernel (4 x mjx.step) and the task kernel (contacts,
-ray grid, obs, rewards, wrappers). N>1: every rank owns its own 4096 envs (index sharding, no collective
+`env.step` over all envs = ONE launch up to 4144 envs per GPU (warp-per-env physics, 4 x mjx.step, with the task layer - contacts,
+ray grid, obs, rewards, wrappers - fused behind it), two above (quad-per-env physics kernel + task kernel). N>1: every rank owns its own 4096 envs (index sharding, no collective
 in the data path) -> weak scaling. BASELINE.md section 3: 50 warm-up + 500 timed steps (the defaults).
 
 Timed regions (device time, CUDA events on the launching stream, max over ranks):
@@ -222,7 +222,7 @@ def workload_config(args, n_per_gpu, n_gpus):
                         f"{'randomize.py on' if args.dr else 'no DR (terrain assignment only)'}, wrapped step (episode + auto-reset), 4 substeps",
             "num_envs_per_gpu": n_per_gpu, "task": args.task, "terrain": args.terrain, "dr": bool(args.dr),
             "actions": "U(-1,1), pool of 16 pre-generated device buffers", "l2": "flushed between timed steps (256 MiB write); value_l2_resident = back-to-back",
-            "launches_per_step": "2 (physics kernel, task kernel)"}
+            "launches_per_step": "1 up to 4144 envs per GPU (warp-per-env physics with the task layer fused behind it), 2 above (quad-per-env physics kernel, task kernel)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,17 +251,25 @@ class Timer:
         return self.max_over_ranks(e0.elapsed_time(e1))
 
     def flushed(self, K):
-        """-> (total ms of the K steps, mean ms of the physics kernel, mean ms of the task kernel)."""
+        """-> (total ms of the K steps, mean ms of the physics kernel, mean ms of the task kernel). A handle whose step is ONE launch
+        (generation 1, task layer fused behind the physics) is timed through the product call `pgtt_step`: the second figure is then the
+        whole fused kernel and the third is 0."""
         torch = self.torch
         if self.flush is None:
             self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
         st = ctypes.c_void_p(self.stream.cuda_stream)
+        fused = self.abi.step_launches() == 1
         self.barrier()
         for i in range(K):
             self.flush.fill_(i & 0xFF)
             p = self.pool[i % len(self.pool)].data_ptr()
             evs[i][0].record(self.stream)
+            if fused:
+                self.abi.step_ptr(p, wrapped=True)
+                evs[i][1].record(self.stream)
+                evs[i][2].record(self.stream)
+                continue
             rc = self.part(self.abi.h, p, 1, 0, st)
             evs[i][1].record(self.stream)
             rc |= self.part(self.abi.h, p, 1, 1, st)
@@ -479,12 +487,12 @@ def main():
         rec = load_kernel_metrics().get(mkey)
         achieved = B_ALG * N / ((physics_ms + task_ms) * 1e-3) / 1e9
         roof = {"bound": "fp32-issue/latency", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "hbm_frac": achieved / peak,
-                "peak_source": peak_src, "kernel": kname, "kernel_ms": physics_ms, "task_kernel": "pgtt_task_kernel<OP_TASK>", "task_kernel_ms": task_ms,
+                "peak_source": peak_src, "kernel": kname, "kernel_ms": physics_ms, "task_kernel": "pgtt_task_kernel<OP_TASK>" if task_ms > 0 else "(fused into the step kernel)", "task_kernel_ms": task_ms,
                 "algorithmic_bytes_per_env_step": B_ALG, "fp32_peak_tflops": fp32_peak,
                 "fp32_peak_source": f"{N_SM} SMs x {FP32_LANES} fp32 lanes x 2 x {sm_mhz:.0f} MHz (median SM clock of this run)",
                 "traffic": None, "fp32_tflops": None, "fp32_frac": None, "metrics_key": mkey,
                 "note": "the step is fp32-issue / latency bound (~170 flop per algorithmic byte; SURVEY 8d, DESIGN.md 3): `frac` (HBM) is reported because the "
-                        "contract asks for it, `fp32_frac` (measured flops of the physics kernel / its live duration / fp32 peak) is the figure that describes it"}
+                        "contract asks for it, `fp32_frac` (measured flops of the step kernel / its live duration / fp32 peak) is the figure that describes it"}
         if rec:
             roof.update({"traffic": rec["dram_bytes_read"] + rec["dram_bytes_write"], "flops_per_launch": rec["fp32_flops"],
                          "fp32_tflops": rec["fp32_flops"] / (physics_ms * 1e-3) / 1e12, "fp32_frac": rec["fp32_flops"] / (physics_ms * 1e-3) / 1e12 / fp32_peak,
@@ -496,7 +504,7 @@ def main():
             "value_l2_resident": total_envs * K / (ms_resident * 1e-3), "ms_per_step_l2_resident": ms_resident / K,
             "e2e": {"value": total_envs * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * 12 * 4, "d2h_bytes_per_step": N * 2 * 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "launches_per_step": abi.step_launches(),
             "rollout": {"value": total_envs * T * n_unroll / (ms_rollout * 1e-3), "unit": UNIT, "unroll_length": T, "unrolls": n_unroll,
                         "ms_per_env_step_batch": ms_rollout / (T * n_unroll), "gpu_launches": int(rollout_launches),
                         "what": "policy MLP 171-512-256-128-24 (tcgen05, bf16 operands, fp32 accumulate - narrower than the reference's fp32 'highest' "

@@ -165,6 +165,8 @@ int64_t pgtt_launch_count(pgtt_env* env);
 /* Which physics kernel this handle launches: 0 = warp-per-env (pgtt_env_kernel), 1 = quad-per-env (pgtt_quad_kernel).
  * Chosen at creation from num_envs (measured crossover) or PGTT_KERNEL=warp|quad. */
 int pgtt_step_kernel_generation(pgtt_env* env);
+/* Kernel launches per pgtt_step: 1 = generation 1 with the task layer fused behind the physics (default; PGTT_FUSE_TASK=0 splits it), 2 = physics kernel + task kernel. */
+int pgtt_step_launches(pgtt_env* env);
 
 /* ---- rollout collector: acting step of brax ppo (training/train.py:135-161,242-263; network spec as re-hosted by
  * deploy/policy_net.py:35-64). One fused tcgen05 kernel: normalise obs -> MLP (swish) -> NormalTanh sample. ---- */

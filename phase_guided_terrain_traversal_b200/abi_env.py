@@ -155,7 +155,12 @@ class AbiEnv:
         return int(self.lib.pgtt_launch_count(self.h))
 
     def step_kernel(self) -> str:
-        return "pgtt_quad_kernel<OP_STEP>" if int(self.lib.pgtt_step_kernel_generation(self.h)) == 1 else "pgtt_env_kernel<OP_STEP>"
+        if int(self.lib.pgtt_step_kernel_generation(self.h)) == 1:
+            return "pgtt_quad_kernel<OP_STEP>"
+        return "pgtt_env_kernel<OP_STEP_TASK>" if self.step_launches() == 1 else "pgtt_env_kernel<OP_STEP>"
+
+    def step_launches(self) -> int:
+        return int(self.lib.pgtt_step_launches(self.h))
 
     # -- host-side convenience (tests) ----------------------------------------------------
     def get(self, name) -> np.ndarray:

@@ -112,7 +112,7 @@ DEV void env_debug_forward(WS& w, const EnvBuffers& B, float* out_all, int env, 
 // ----------------------------------------------------------------------------------------------
 // kernels / launch shims
 // ----------------------------------------------------------------------------------------------
-enum { OP_STEP = 0, OP_RESET, OP_FORWARD, OP_DEBUG, OP_TASK, OP_SCAN };   // OP_TASK / OP_SCAN run in the task kernel
+enum { OP_STEP = 0, OP_RESET, OP_FORWARD, OP_DEBUG, OP_TASK, OP_SCAN, OP_STEP_TASK };   // OP_TASK / OP_SCAN run in the task kernel; OP_STEP_TASK = physics + task in one launch (generation 1)
 struct LaunchArgs {
   EnvBuffers B;
   int op, wrapped;
@@ -137,6 +137,7 @@ DEV void dispatch(WS& w, TaskWS& t, const LaunchArgs& a, int env, int lane) {
     case OP_DEBUG: env_debug_forward(w, a.B, a.out, env, lane); break;
     case OP_TASK: task_step(t, a.B, a.action, env, lane, a.wrapped, a.rec); break;
     case OP_SCAN: task_scan(t, a.B, a.center, a.yaw, a.out, env, lane); break;
+    case OP_STEP_TASK: env_physics(w, a.B, a.action, env, lane); task_step(t, a.B, a.action, env, lane, a.wrapped, a.rec); break;
   }
 }
 
@@ -164,6 +165,18 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, ENV_CTAS_PER_SM) pgt
     syncwarp();
   }
   if (OP == OP_STEP) env_physics(w, a.B, a.action, env, lane, reinterpret_cast<long long*>(a.out));
+  else if (OP == OP_STEP_TASK) {
+    // the whole control step in one launch: the task layer of THIS env right behind its physics, in the same warp. The physics
+    // workspace is dead by then, so the task workspace aliases it; mjx.Data travels through the handle's buffers exactly as between the
+    // two kernels (same warp: __syncwarp orders its global writes before its reads). A CTA barrier keeps the warps of the SM in step
+    // on the task layer's instruction stream as well.
+    static_assert(sizeof(TaskWS) <= sizeof(WS), "the task workspace must fit the physics workspace it aliases");
+    const int bar_threads = w.bar_threads;
+    env_physics(w, a.B, a.action, env, lane, nullptr);
+    syncwarp();
+    cta_bar(bar_threads);
+    task_step(*reinterpret_cast<TaskWS*>(&w), a.B, a.action, env, lane, a.wrapped, a.rec);
+  }
   else if (OP == OP_RESET) {
     TaskWS& t = *reinterpret_cast<TaskWS*>(reinterpret_cast<char*>(smem4) + (size_t)wpb * WS_BYTES + (size_t)warp * TASK_BYTES);
     env_reset(w, t, a.B, a.keys, env, lane);
@@ -227,6 +240,7 @@ static void quad_entry(void* p, int lane) {
 struct pgtt_env {
   int device, N, wpb;
   int quad;   // 1: generation-2 quad-per-env physics kernel for step / debug-forward, 0: warp-per-env (PGTT_KERNEL=warp|quad overrides)
+  int fuse_task;   // generation 1: the task layer runs behind the physics in the same launch (PGTT_FUSE_TASK=0|1 overrides)
   ModelConst mc;
   EnvBuffers B;
   std::vector<void*> allocs;
@@ -326,6 +340,7 @@ static int launch(pgtt_env* e, LaunchArgs& a, void* stream) {
     const size_t smem = wpb * WS_BYTES;
     switch (a.op) {
       case OP_STEP: pgtt_env_kernel<OP_STEP><<<blocks, wpb * 32, smem, st>>>(a); break;
+      case OP_STEP_TASK: pgtt_env_kernel<OP_STEP_TASK><<<blocks, wpb * 32, smem, st>>>(a); break;
       case OP_RESET: pgtt_env_kernel<OP_RESET><<<blocks, wpb * 32, smem + wpb * TASK_BYTES, st>>>(a); break;
       case OP_FORWARD: pgtt_env_kernel<OP_FORWARD><<<blocks, wpb * 32, smem, st>>>(a); break;
       default: pgtt_env_kernel<OP_DEBUG><<<blocks, wpb * 32, smem, st>>>(a); break;
@@ -400,6 +415,7 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
     CUDA_OK(cudaSetDevice(device));
     const size_t smem = MAX_WARPS_PER_BLOCK * WS_BYTES;
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_STEP_TASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RESET_WARPS * (WS_BYTES + TASK_BYTES))));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(pgtt_env_kernel<OP_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -430,6 +446,10 @@ int pgtt_create(const pgtt_model_desc* m, const pgtt_task_desc* t, int device, i
     e->quad = num_envs > n_sm * MAX_WARPS_PER_BLOCK * ENV_CTAS_PER_SM;
   }
   if (const char* k = getenv("PGTT_KERNEL")) e->quad = strcmp(k, "quad") == 0;
+  // generation 1 runs the task layer behind the physics in the same launch: -2 % per step at 4096 envs (no second launch, no reload of
+  // mjx.Data, SMs that finish their physics early start their task layer early; profiles/r02_summary.md)
+  e->fuse_task = 1;
+  if (const char* f = getenv("PGTT_FUSE_TASK")) e->fuse_task = atoi(f) != 0;
   ModelConst& c = e->mc;
   memset(&c, 0, sizeof(c));
   c.dt = (float)m->timestep; c.gravity_z = (float)m->gravity[2]; c.impratio = (float)m->impratio;
@@ -640,6 +660,11 @@ int pgtt_step_record(pgtt_env* e, const float* action, int wrapped, float* os, f
   LaunchArgs a; memset(&a, 0, sizeof(a));
   a.op = OP_STEP; a.action = action; a.wrapped = wrapped;
   a.rec.obs_state = os; a.rec.obs_priv = op; a.rec.reward = rw; a.rec.discount = dc; a.rec.truncation = tr;
+  if (!e->quad && e->fuse_task) {                 // generation 1: physics + task layer in one launch
+    a.op = OP_STEP_TASK;
+    if (int rc = launch(e, a, stream)) return rc;
+    return mark_launched(e, stream);
+  }
   if (int rc = launch(e, a, stream)) return rc;   // physics: n_substeps x mjx.step
   a.op = OP_TASK;
   if (int rc = launch(e, a, stream)) return rc;   // task layer, wrappers, transition slot
@@ -707,6 +732,7 @@ int pgtt_obs_dims(pgtt_env* e, int* nobs, int* npriv) {
   return PGTT_OK;
 }
 int pgtt_step_kernel_generation(pgtt_env* e) { return e ? e->quad : -1; }
+int pgtt_step_launches(pgtt_env* e) { return e ? ((!e->quad && e->fuse_task) ? 1 : 2) : -1; }
 // graph replays of the rollout launch this handle's kernels without going through launch(): keep the counter honest
 void pgtt_internal_count_launches(pgtt_env* e, int64_t n) { if (e) e->launches += n; }
 

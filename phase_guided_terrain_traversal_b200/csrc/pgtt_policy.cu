@@ -30,6 +30,7 @@
 
 // pgtt_api.cu (not part of the ABI header)
 extern "C" void pgtt_internal_count_launches(pgtt_env* env, int64_t n);
+extern "C" int pgtt_step_launches(pgtt_env* env);
 extern "C" int pgtt_internal_make_resident(pgtt_env* env, void* stream);
 extern "C" int pgtt_internal_mark_launched(pgtt_env* env, void* stream);
 extern "C" uint64_t pgtt_internal_serial(pgtt_env* env);   // unique per pgtt_create: a handle re-created at the same address is a different env
@@ -1122,7 +1123,7 @@ int pgtt_rollout(pgtt_env* env, pgtt_policy* pol, int T, uint64_t seed, uint64_t
     }
     pol->gkey.env = env; pol->gkey.env_serial = pgtt_internal_serial(env); pol->gkey.T = T; pol->gkey.deterministic = deterministic; pol->gkey.seed = seed; pol->gkey.o = *o;
   } else {
-    pgtt_internal_count_launches(env, 2 * (int64_t)T);   // capture counted the first unroll's launches
+    pgtt_internal_count_launches(env, (int64_t)pgtt_step_launches(env) * T);   // capture counted the first unroll's launches
     pol->launches += T;
   }
   PCUDA(cudaEventRecord(pol->ev_in, user));

@@ -55,7 +55,7 @@ class RolloutCollector:
 
     def collect(self, state=None, deterministic: bool = False) -> tuple:
         """Runs `unroll_length` control steps from the env's current state; returns (final state, Rollout).
-        One native call (`pgtt_rollout`): 1 + 3 T kernel launches on the current stream, nothing returns to the host."""
+        One native call (`pgtt_rollout`): 1 + T x (policy + the step's one or two) kernel launches on the current stream, nothing returns to the host."""
         buf = self.buf
         if state is not None and not (state._live and state._owner is self.env):
             self.env.set_state(state)
@@ -69,4 +69,4 @@ class RolloutCollector:
         return self.env._live_state(), buf
 
     def launches_per_collect(self) -> int:
-        return 1 + self.T * 3
+        return 1 + self.T * (1 + self.abi.step_launches())

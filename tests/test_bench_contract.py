@@ -51,17 +51,18 @@ def test_b200_arm_line_carries_roofline_baseline_e2e_and_clocks():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert (KEYS - {"impl"}) | {"roofline", "gpu_launches", "clocks", "rollout", "config2", "strong", "train_step"} <= set(d)
-    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["scaling"] == "weak" and d["gpu_launches"] == 40   # physics + task kernel per step
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["scaling"] == "weak" and d["launches_per_step"] in (1, 2)
+    assert d["gpu_launches"] == 20 * d["launches_per_step"]   # 4096 envs: one fused launch per step (PGTT_FUSE_TASK=0: physics + task kernel)
     r = d["roofline"]
     assert r["bound"] == "fp32-issue/latency" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["kernel"].startswith("pgtt_")
-    assert r["hbm_frac"] == r["frac"] and 0 < r["kernel_ms"] < d["ms_per_step"] and 60 < r["fp32_peak_tflops"] < 80
+    assert r["hbm_frac"] == r["frac"] and 0 < r["kernel_ms"] <= d["ms_per_step"] * 1.001 and 60 < r["fp32_peak_tflops"] < 80
     if r["traffic"] is not None:     # a committed ncu record exists for this configuration: measured flops, not an estimate
         assert (ROOT / r["metrics_file"]).exists() and 0 < r["fp32_frac"] < 1 and r["traffic"] > 0 and r["flops_per_launch"] > 1e8
     assert 0 <= d["health"]["auto_reset_fraction"] < 0.2
     assert d["config2"]["num_envs_per_gpu"] == 8192 and d["config2"]["dr"] is True and d["config2"]["value"] > 0 and d["config2"]["state_finite"]
     assert d["strong"]["total_envs"] == 32768 and d["strong"]["value"] > 0
     assert "unavailable" in d["train_step"] or d["train_step"]["value"] > 0
-    assert d["rollout"]["gpu_launches"] == 3 * d["rollout"]["unroll_length"] * d["rollout"]["unrolls"] + d["rollout"].get("extra_launches", 0)
+    assert d["rollout"]["gpu_launches"] == (1 + d["launches_per_step"]) * d["rollout"]["unroll_length"] * d["rollout"]["unrolls"] + d["rollout"].get("extra_launches", 0)
     assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 12 * 4 and d["e2e"]["d2h_bytes_per_step"] == 4096 * 2 * 4 and 0 < d["e2e"]["value"] <= d["value"] * 1.05
     assert d["cpu_baseline"]["kind"] == "port" and 0 < d["cpu_baseline"]["value"] < d["value"] / 10      # the north-star's >= 10x
     assert d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}

@@ -564,7 +564,7 @@ def test_baseline_sizes_against_the_oracle(cfgname, n, level, dyn, train_cfg):
     keys = keys_for(n, 21)
     orc = Oracle(m, train_cfg, n, "f32")
     env = make_env("cuda-auto", m, train_cfg, n)
-    assert env.step_kernel() == ("pgtt_quad_kernel<OP_STEP>" if n > 4144 else "pgtt_env_kernel<OP_STEP>")
+    assert env.step_kernel() == ("pgtt_quad_kernel<OP_STEP>" if n > 4144 else "pgtt_env_kernel<OP_STEP_TASK>")   # (one fused launch per step below one resident wave)
     orc.randomize(keys, table, dyn); env.set_terrain(table); env.randomize(keys, dyn)
     assert np.array_equal(orc.get("terrain_index")[:, 0], env.get("terrain_index")[:, 0])
     orc.reset(keys + 2); env.reset(keys + 2)
