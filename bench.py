@@ -277,6 +277,9 @@ class Timer:
             if rc:
                 raise RuntimeError("pgtt_internal_step_part failed")
         self.barrier()
+        if fused:
+            tot = [e[0].elapsed_time(e[1]) for e in evs]
+            return self.max_over_ranks(float(sum(tot))), float(np.mean(tot)), 0.0
         tot = [e[0].elapsed_time(e[2]) for e in evs]
         return self.max_over_ranks(float(sum(tot))), float(np.mean([e[0].elapsed_time(e[1]) for e in evs])), float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
 
