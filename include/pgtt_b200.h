@@ -220,6 +220,12 @@ int pgtt_gae(const float* truncation, const float* discount, const float* reward
 long long pgtt_col_moments_scratch_doubles(int cols);
 int pgtt_col_moments(const float* x, long long rows, int cols, int ld, double* out, double* scratch, void* stream);
 
+/* The multi-rank form of pgtt_gae_moments (the north-star's advantage-normalisation all-reduce): pgtt_gae_sums leaves this rank's (count, sum, sum of squares)
+ * of the advantages in sums3 (DEVICE double [3]); the caller all-reduces them (NCCL, SUM) and pgtt_moments_finalize writes moments [2] = (mean, std) of ALL ranks. */
+int pgtt_gae_sums(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
+                  float reward_scaling, float* vs, float* adv, double* sums3, void* stream);
+int pgtt_moments_finalize(const double* sums3, float* moments, void* stream);
+
 /* Everything of minibatch number *mbi that is not an observation, in one launch (all DEVICE): idx [mb] = perm[*mbi][:] (int64 segment ids, also what
  * pgtt_mlp_forward_gather takes), raw [T][mb][A] from raw_all [T][S][A], scal [n_scal][T][mb] from scal_all [n_scal][T][S], eps [T][mb][A] = eps_all[*mbi]
  * (brax `sgd_step`: shuffle, reshape into minibatches, slice; training/train.py:135-161). *mbi is read on the device, so a captured graph serves every minibatch. */

@@ -208,6 +208,8 @@ def declare(lib):
         lib.pgtt_col_moments_scratch_doubles.argtypes = [C.c_int]
         lib.pgtt_col_moments_scratch_doubles.restype = C.c_longlong
         lib.pgtt_col_moments.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, vp, vp, vp]
+        lib.pgtt_gae_sums.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+        lib.pgtt_moments_finalize.argtypes = [vp, vp, vp]
         lib.pgtt_minibatch_gather.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.pgtt_gae_moments.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
         lib.pgtt_ppo_head.argtypes = [vp] * 8 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
@@ -237,7 +239,7 @@ ABI_SYMBOLS = [
     "pgtt_last_error", "pgtt_version", "pgtt_create", "pgtt_destroy", "pgtt_sync", "pgtt_set_terrain_table", "pgtt_randomize",
     "pgtt_reset", "pgtt_step", "pgtt_step_record", "pgtt_forward", "pgtt_heightscan", "pgtt_get_buffers", "pgtt_obs_dims", "pgtt_debug_forward", "pgtt_launch_count", "pgtt_record", "pgtt_step_kernel_generation", "pgtt_step_launches",
     "pgtt_policy_last_error", "pgtt_policy_create", "pgtt_policy_destroy", "pgtt_policy_set_params", "pgtt_policy_set_params_device", "pgtt_policy_act",
-    "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_gae_moments", "pgtt_minibatch_gather", "pgtt_col_moments_scratch_doubles", "pgtt_col_moments", "pgtt_ppo_head", "pgtt_adam_clip", "pgtt_adam_scratch_floats",
+    "pgtt_policy_launch_count", "pgtt_rollout", "pgtt_gae", "pgtt_gae_moments", "pgtt_gae_sums", "pgtt_moments_finalize", "pgtt_minibatch_gather", "pgtt_col_moments_scratch_doubles", "pgtt_col_moments", "pgtt_ppo_head", "pgtt_adam_clip", "pgtt_adam_scratch_floats",
     "pgtt_learner_last_error", "pgtt_linear_forward", "pgtt_linear_backward_input", "pgtt_linear_backward_params_splits", "pgtt_linear_backward_params_scratch", "pgtt_linear_backward_params", "pgtt_silu_backward",
     "pgtt_mlp_last_error", "pgtt_mlp_create", "pgtt_mlp_destroy", "pgtt_mlp_rows", "pgtt_mlp_forward", "pgtt_mlp_forward_gather", "pgtt_mlp_backward", "pgtt_mlp_debug_trace",
 ]

@@ -801,8 +801,9 @@ int64_t pgtt_policy_launch_count(pgtt_policy* p) { return p ? p->launches : 0; }
 // deviations), every partial sum in a fixed order - what ppo_loss normalises the advantages with.
 __global__ void pgtt_gae_kernel(const float* __restrict__ trunc, const float* __restrict__ disc, const float* __restrict__ rew,
                                 const float* __restrict__ val, int T, int B, float lam, float gamma, float rscale,
-                                float* __restrict__ vs, float* __restrict__ adv, float* __restrict__ mom) {
+                                float* __restrict__ vs, float* __restrict__ adv, float* __restrict__ mom, double* __restrict__ sums3) {
   __shared__ float red[33];
+  __shared__ double dred[2][32];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float asum = 0.f;
   if (b < B) {
@@ -820,6 +821,19 @@ __global__ void pgtt_gae_kernel(const float* __restrict__ trunc, const float* __
       vs[i] = vst;
       vs_next = vst;
     }
+  }
+  if (sums3) {        // multi-rank: (count, sum, sum of squares) of this rank's advantages in float64; the ranks add them up (NCCL) and pgtt_moments_finalize forms mean / std
+    double s1 = 0.0, s2 = 0.0;
+    if (b < B) for (int t = 0; t < T; t++) { const double a = (double)adv[(size_t)t * B + b]; s1 += a; s2 += a * a; }
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { dred[0][threadIdx.x >> 5] = s1; dred[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int w = 0; w < (int)((blockDim.x + 31) / 32); w++) { a1 += dred[0][w]; a2 += dred[1][w]; }
+      sums3[0] = (double)T * (double)B; sums3[1] = a1; sums3[2] = a2;
+    }
+    return;
   }
   if (!mom) return;                                          // (uniform)
   auto block_sum = [&](float v) -> float {
@@ -846,7 +860,28 @@ __global__ void pgtt_gae_kernel(const float* __restrict__ trunc, const float* __
 int pgtt_gae(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
              float reward_scaling, float* vs, float* adv, void* stream) {
   if (!truncation || !discount || !reward || !values || !vs || !adv || T <= 0 || B <= 0) return pfail(PGTT_ERR_ARG, "pgtt_gae: null argument or empty shape");
-  pgtt_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, nullptr);
+  pgtt_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, nullptr, nullptr);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+
+// multi-rank variant of pgtt_gae_moments: this rank's (count, sum, sum of squares) of the advantages, float64, from the same launch; after the all-reduce
+// pgtt_moments_finalize turns the global sums into (mean, std)
+int pgtt_gae_sums(const float* truncation, const float* discount, const float* reward, const float* values, int T, int B, float lambda, float gamma,
+                  float reward_scaling, float* vs, float* adv, double* sums3, void* stream) {
+  if (!truncation || !discount || !reward || !values || !vs || !adv || !sums3 || T <= 0 || B <= 0) return pfail(PGTT_ERR_ARG, "pgtt_gae_sums: null argument or empty shape");
+  if (B > 1024) return pfail(PGTT_ERR_ARG, "pgtt_gae_sums: more than 1024 segments per minibatch");
+  pgtt_gae_kernel<<<1, (B + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, nullptr, sums3);
+  PCUDA(cudaGetLastError());
+  return PGTT_OK;
+}
+__global__ void pgtt_moments_finalize_kernel(const double* __restrict__ s, float* __restrict__ mom) {
+  const double mean = s[1] / s[0], var = s[2] / s[0] - mean * mean;
+  mom[0] = (float)mean; mom[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+}
+int pgtt_moments_finalize(const double* sums3, float* moments, void* stream) {
+  if (!sums3 || !moments) return pfail(PGTT_ERR_ARG, "pgtt_moments_finalize: null argument");
+  pgtt_moments_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums3, moments);
   PCUDA(cudaGetLastError());
   return PGTT_OK;
 }
@@ -855,7 +890,7 @@ int pgtt_gae_moments(const float* truncation, const float* discount, const float
                      float reward_scaling, float* vs, float* adv, float* moments, void* stream) {
   if (!truncation || !discount || !reward || !values || !vs || !adv || !moments || T <= 0 || B <= 0) return pfail(PGTT_ERR_ARG, "pgtt_gae_moments: null argument or empty shape");
   if (B > 1024) return pfail(PGTT_ERR_ARG, "pgtt_gae_moments: more than 1024 segments per minibatch (use pgtt_gae and reduce separately)");
-  pgtt_gae_kernel<<<1, (B + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, moments);
+  pgtt_gae_kernel<<<1, (B + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(truncation, discount, reward, values, T, B, lambda, gamma, reward_scaling, vs, adv, moments, nullptr);
   PCUDA(cudaGetLastError());
   return PGTT_OK;
 }

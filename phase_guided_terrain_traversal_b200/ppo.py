@@ -677,7 +677,7 @@ class PPOTrainer:
                 off += p_.numel()
             L = len(self.policy_params[0])
             mk = lambda ks, rows: _MlpHandle(lib, (ks[0].shape[0], *[k.shape[1] for k in ks]), rows, dev.index)
-            self._nb = {"logits": f(T * mb, 24), "base_all": f((T + 1) * mb), "vs": f(T, mb), "adv": f(T, mb), "mom": f(2), "g_logits": f(T * mb, 24),
+            self._nb = {"logits": f(T * mb, 24), "base_all": f((T + 1) * mb), "vs": f(T, mb), "adv": f(T, mb), "mom": f(2), "sums3": torch.zeros(3, dtype=torch.float64, device=dev), "g_logits": f(T * mb, 24),
                         "g_base_all": torch.zeros((T + 1) * mb, dtype=torch.float32, device=dev), "sums": f(4), "flat_g": flat_g,
                         "g_pol": (views[:L], views[L:2 * L]), "g_val": (views[2 * L:3 * L], views[3 * L:]),
                         "h_pol": mk(self.policy_params[0], T * mb), "h_val": mk(self.value_params[0], (T + 1) * mb),
@@ -707,9 +707,10 @@ class PPOTrainer:
         cur.wait_stream(side)
         gae_args = (scal[3].data_ptr(), scal[2].data_ptr(), scal[1].data_ptr(), nb["base_all"].data_ptr(), T, mb, cfg.gae_lambda, cfg.discounting, cfg.reward_scaling,
                     nb["vs"].data_ptr(), nb["adv"].data_ptr())
-        if cfg.global_advantage_norm and self.world > 1:
-            chk(lib.pgtt_gae(*gae_args, st(cur)), lib.pgtt_policy_last_error)
-            nb["mom"].copy_(torch.stack(self._moments(nb["adv"])).to(torch.float32))
+        if cfg.global_advantage_norm and self.world > 1:     # the advantage-normalisation all-reduce: three float64 sums per rank
+            chk(lib.pgtt_gae_sums(*gae_args, nb["sums3"].data_ptr(), st(cur)), lib.pgtt_policy_last_error)
+            torch.distributed.all_reduce(nb["sums3"], group=self.group)
+            chk(lib.pgtt_moments_finalize(nb["sums3"].data_ptr(), nb["mom"].data_ptr(), st(cur)), lib.pgtt_policy_last_error)
         else:
             chk(lib.pgtt_gae_moments(*gae_args, nb["mom"].data_ptr(), st(cur)), lib.pgtt_policy_last_error)
         chk(lib.pgtt_ppo_head(nb["logits"].data_ptr(), nb["base_all"].data_ptr(), raw.data_ptr(), scal[0].data_ptr(), nb["adv"].data_ptr(), nb["vs"].data_ptr(), eps.data_ptr(),

@@ -508,3 +508,37 @@ def test_column_moment_kernel_matches_float64_statistics():
     b.update(store[:20, :, :171].cpu().to("cuda").contiguous()[:, :64])                  # small batches take the generic path ...
     b.update(store[:20, :, :171].contiguous()[:, 64:])                                  # ... large ones the kernel: merged statistics agree
     assert float((a.mean - b.mean).abs().max()) < 1e-12 and float((a.std - b.std).abs().max()) < 1e-10
+
+
+@pytest.mark.gpu
+def test_gae_moment_variants_agree():
+    """`pgtt_gae_moments` (single rank: mean / std inside the GAE launch) against `pgtt_gae_sums` + `pgtt_moments_finalize` (multi-rank form: float64 sums,
+    all-reduce in between - here one rank) and against torch on the advantages the plain `pgtt_gae` writes: same vs / adv bit for bit, moments to 1e-6."""
+    import ctypes as C
+    import torch
+    from phase_guided_terrain_traversal_b200 import _native as nat
+    lib = nat.load_library()
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    T, B = 20, 256
+    r = lambda *s: torch.randn(s, device="cuda", generator=g)
+    trunc = (torch.rand((T, B), device="cuda", generator=g) < 0.02).float()
+    disc = 1.0 - (torch.rand((T, B), device="cuda", generator=g) < 0.05).float()
+    rew, val = r(T, B).abs(), r(T + 1, B)
+    out = {}
+    for kind in ("plain", "moments", "sums"):
+        vs, adv, mom = torch.empty(T, B, device="cuda"), torch.empty(T, B, device="cuda"), torch.zeros(2, device="cuda")
+        sums = torch.zeros(3, dtype=torch.float64, device="cuda")
+        args = (trunc.data_ptr(), disc.data_ptr(), rew.data_ptr(), val.data_ptr(), T, B, 0.95, 0.97, 1.0, vs.data_ptr(), adv.data_ptr())
+        if kind == "plain":
+            assert lib.pgtt_gae(*args, None) == 0
+            mom = torch.stack([adv.mean(), adv.std(unbiased=False)])
+        elif kind == "moments":
+            assert lib.pgtt_gae_moments(*args, mom.data_ptr(), None) == 0
+        else:
+            assert lib.pgtt_gae_sums(*args, sums.data_ptr(), None) == 0
+            assert lib.pgtt_moments_finalize(sums.data_ptr(), mom.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        out[kind] = (vs, adv, mom)
+    for kind in ("moments", "sums"):
+        assert torch.equal(out[kind][0], out["plain"][0]) and torch.equal(out[kind][1], out["plain"][1])
+        assert float((out[kind][2] - out["plain"][2]).abs().max()) < 1e-6, (kind, out[kind][2], out["plain"][2])
