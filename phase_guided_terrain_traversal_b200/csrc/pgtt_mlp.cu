@@ -388,11 +388,6 @@ struct pgtt_mlp {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 static int launch_bgemm(const BGemm& g, int m_blocks, int n_tiles, int splits, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    MCUDA(cudaFuncSetAttribute(pgtt_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM));
-    attr = true;
-  }
   pgtt_bgemm_kernel<<<dim3(m_blocks, n_tiles, splits), BG_THREADS, BG_SMEM, st>>>(g);
   MCUDA(cudaGetLastError());
   return PGTT_OK;
@@ -416,6 +411,7 @@ int pgtt_mlp_create(int n_layers, const int* dims, int rows, int device, pgtt_ml
   if (!dims || !out || n_layers < 1 || n_layers >= MLP_MAX_LAYERS || rows < 1) return mfail(PGTT_ERR_ARG, "pgtt_mlp_create: bad argument");
   for (int i = 0; i <= n_layers; i++) if (dims[i] < 1 || dims[i] > 4096) return mfail(PGTT_ERR_ARG, "pgtt_mlp_create: layer widths must be in 1..4096");
   MCUDA(cudaSetDevice(device));
+  MCUDA(cudaFuncSetAttribute(pgtt_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM));   // (per device: every handle asks for it)
   pgtt_mlp* m = new pgtt_mlp();
   m->L = n_layers; m->rows = rows; m->device = device; m->nrb = cdiv(rows, 128); m->forward_done = false;
   m->trace = nullptr; m->trace_on = 0; m->n_launch = 0; m->aux = nullptr;
@@ -476,6 +472,7 @@ int pgtt_mlp_create(int n_layers, const int* dims, int rows, int device, pgtt_ml
 
 void pgtt_mlp_destroy(pgtt_mlp* m) {
   if (!m) return;
+  cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   for (void* p : m->allocs) cudaFree(p);
   for (int i = 0; i < MLP_MAX_LAYERS + 2; i++) if (m->ev[i]) cudaEventDestroy(m->ev[i]);

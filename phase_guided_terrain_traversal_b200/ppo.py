@@ -294,6 +294,8 @@ def _native_mlp():
                 if h is None:
                     if torch.cuda.is_current_stream_capturing():
                         raise RuntimeError("pgtt_mlp handle for a new (network, rows) requested inside CUDA graph capture: run one eager step first")
+                    while len(_MLP_HANDLES) >= 8:          # bounded: the oldest workspace goes (handles hold ~100 MB of device memory each)
+                        _MLP_HANDLES.pop(next(iter(_MLP_HANDLES)))
                     h = _MLP_HANDLES[key] = _MlpHandle(lib, dims, rows, dev.index)
                 y = torch.empty((rows, dims[-1]), device=dev, dtype=torch.float32)
                 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
