@@ -297,8 +297,13 @@ __global__ void __launch_bounds__(BG_THREADS, 1) pgtt_bgemm_kernel(BGemm g) {
         float* o = g.out + ((size_t)(g.mode == EP_PART ? split : 0) * g.Mc + row) * g.ldo + col0;
         const bool vec = ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && col0 + 32 <= g.Nc;
         if (g.bias) {
+          if (col0 + 32 <= g.Nc && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; i++) if (col0 + i < g.Nc) v[i] += __ldg(g.bias + col0 + i);
+            for (int i = 0; i < 32; i += 4) { const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + i)); v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) if (col0 + i < g.Nc) v[i] += __ldg(g.bias + col0 + i);
+          }
         }
         if (vec) {
 #pragma unroll
@@ -309,43 +314,57 @@ __global__ void __launch_bounds__(BG_THREADS, 1) pgtt_bgemm_kernel(BGemm g) {
         }
       } else if (row_ok) {
         float* zr = g.z + z_off(row, col0, g.ldz);          // (ldz = float4 groups per row)
+        const bool full = col0 + 32 <= g.Nc;                // (warp-uniform) every column of the group is valid: no per-element predicates
         if (g.mode == EP_HIDDEN) {                            // z = acc + b (kept), y = SiLU(z)
+          if (full && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = (col0 + i < g.Nc) ? v[i] + __ldg(g.bias + col0 + i) : 0.f;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + i));     // (col0 is a multiple of 32)
+              v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+              *reinterpret_cast<float4*>(zr + i * 32) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) if (col0 + i < g.Nc) *reinterpret_cast<float4*>(zr + i * 32) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 32; i++) v[i] = (col0 + i < g.Nc) ? v[i] + __ldg(g.bias + col0 + i) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) if (col0 + i < g.Nc) *reinterpret_cast<float4*>(zr + i * 32) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
         } else {                                              // EP_DX: dz = acc * SiLU'(z)
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + i < g.Nc) t = *reinterpret_cast<const float4*>(zr + i * 32);
+            if (full || col0 + i < g.Nc) t = *reinterpret_cast<const float4*>(zr + i * 32);
             const float zz[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               const float sg = __fdividef(1.f, 1.f + __expf(-zz[k]));
-              v[i + k] = (col0 + i + k < g.Nc) ? v[i + k] * (sg * (1.f + zz[k] * (1.f - sg))) : 0.f;
+              const float d = v[i + k] * (sg * (1.f + zz[k] * (1.f - sg)));
+              v[i + k] = (full || col0 + i + k < g.Nc) ? d : 0.f;
             }
           }
         }
-        // blocked split outputs: four octets in both variants
+        // blocked split outputs, four octets in both variants. col0 is a multiple of 32, so the four octets are consecutive k-cores (variant C: 2 KB apart)
+        // respectively consecutive M/N-cores (variant R: 128 B apart) of one chunk: two base addresses, constant offsets
+        const int c80 = col0 >> 3;
+        uint8_t* pc = g.outC + bs_off_C(row, c80, g.out_ncb);
+        uint8_t* pr = g.outR + bs_off_R(row, c80, g.out_ncb);
+        const int ones_o8 = (g.ones_col >= col0 && g.ones_col < col0 + 32) ? ((g.ones_col - col0) >> 3) : -1;   // the octet that holds the column of ones, if any
+        const int n_oct = min(4, g.out_ncb * 16 - c80);
 #pragma unroll
         for (int o8 = 0; o8 < 4; o8++) {
-          const int c8 = (col0 >> 3) + o8;
-          if (c8 < g.out_ncb * 16) {
+          if (o8 < n_oct) {
             uint4 hi, lo;
             split8(v + 8 * o8, &hi, &lo);
-            uint8_t* d = g.outC + bs_off_C(row, c8, g.out_ncb);
-            *reinterpret_cast<uint4*>(d) = hi; *reinterpret_cast<uint4*>(d + BS_PART_BYTES) = lo;
-            if (g.ones_col >= c8 * 8 && g.ones_col < c8 * 8 + 8) {     // the column of ones lives in this octet
+            *reinterpret_cast<uint4*>(pc + o8 * 2048) = hi; *reinterpret_cast<uint4*>(pc + o8 * 2048 + BS_PART_BYTES) = lo;
+            if (o8 == ones_o8) {
               float t[8];
 #pragma unroll
-              for (int i = 0; i < 8; i++) t[i] = (c8 * 8 + i == g.ones_col) ? 1.f : v[8 * o8 + i];
+              for (int i = 0; i < 8; i++) t[i] = (col0 + 8 * o8 + i == g.ones_col) ? 1.f : v[8 * o8 + i];
               split8(t, &hi, &lo);
             }
-            d = g.outR + bs_off_R(row, c8, g.out_ncb);
-            *reinterpret_cast<uint4*>(d) = hi; *reinterpret_cast<uint4*>(d + BS_PART_BYTES) = lo;
+            *reinterpret_cast<uint4*>(pr + o8 * 128) = hi; *reinterpret_cast<uint4*>(pr + o8 * 128 + BS_PART_BYTES) = lo;
           }
         }
       }
