@@ -528,7 +528,7 @@ static int mlp_forward(pgtt_mlp* m, const SplitJob& input, const float* const* w
     SplitJob& jw = J.j[l + 1];
     jw.src = w[l]; jw.rows = m->dims[l]; jw.cols = m->dims[l + 1]; jw.ld = m->dims[l + 1]; jw.dstC = m->wC[l]; jw.dstR = m->wR[l]; jw.ncb = m->w_ncb[l]; jw.ones_col = -1;
   }
-  pgtt_bsplit_kernel<<<dim3(148, m->L + 1), 256, 0, st>>>(J);
+  pgtt_bsplit_kernel<<<dim3(592, m->L + 1), 256, 0, st>>>(J);   // (the input job is ~150 k octets: one grid-stride pass)
   MCUDA(cudaGetLastError());
   for (int l = 0; l < m->L; l++) {
     const int K = m->dims[l], N = m->dims[l + 1];
@@ -581,7 +581,7 @@ int pgtt_mlp_backward(pgtt_mlp* m, const float* dy, float* const* dw, float* con
   for (int l = 0; l < L; l++) if (!dw[l] || !db[l]) return mfail(PGTT_ERR_ARG, "pgtt_mlp_backward: null gradient");
   SplitJobs J = {};
   { SplitJob& jd = J.j[0]; jd.src = dy; jd.rows = m->rows; jd.cols = m->dims[L]; jd.ld = m->dims[L]; jd.dstC = m->dzC[L - 1]; jd.dstR = m->dzR[L - 1]; jd.ncb = m->dz_ncb[L - 1]; jd.ones_col = -1; }
-  pgtt_bsplit_kernel<<<dim3(148, 1), 256, 0, st>>>(J);
+  pgtt_bsplit_kernel<<<dim3(296, 1), 256, 0, st>>>(J);
   MCUDA(cudaGetLastError());
   size_t part_off = 0;
   for (int l = L - 1; l >= 0; l--) {
