@@ -669,7 +669,6 @@ class PPOTrainer:
         from . import _native as nat
         torch, cfg, lib, dev = self.torch, self.cfg, nat.load_library(), self.dev
         T, mb = cfg.unroll_length, self.mb
-        nobs, npriv = self.abi.nobs, self.abi.npriv
         if self._nb is None:
             f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
             flat_g = torch.zeros_like(self.flat_opt.flat)
@@ -959,7 +958,7 @@ def train(environment, wrap_env_fn, randomization_fn, rng_keys, cfg: PPOConfig, 
     per_step = cfg.unroll_length * cfg.batch_size * cfg.num_minibatches
     if not _rank0_says(eval_env is not None, trainer):       # (only rank 0 needs an eval env: brax evaluates on process 0)
         steps = num_training_steps if num_training_steps is not None else max(1, math.ceil(cfg.num_timesteps / per_step))
-        for it in range(steps):
+        for _ in range(steps):
             m = trainer.training_step()
             stop = progress_fn(trainer.env_steps, m) if progress_fn is not None else False
             if policy_params_fn is not None:
@@ -976,8 +975,8 @@ def train(environment, wrap_env_fn, randomization_fn, rng_keys, cfg: PPOConfig, 
         m = evaluator.run_evaluation({})
         if progress_fn is not None:
             progress_fn(0, m)
-    for ep in range(epochs):
-        for it in range(steps_per_epoch):
+    for _ in range(epochs):
+        for _ in range(steps_per_epoch):
             tm = trainer.training_step()
         stop = False
         if evaluator is not None:
