@@ -204,3 +204,20 @@ def test_abi_rejects_bad_arguments_without_touching_a_device():
     assert lib.pgtt_ppo_head(*([null] * 8), 0, 12, 0.3, 0.01, 0.001, null, null, null, null) == -1
     assert lib.pgtt_adam_clip(*([null] * 6), 0, 3e-4, 0.9, 0.999, 1e-8, 1.0, 1.0, null) == -1 and b"pgtt_adam_clip" in lib.pgtt_policy_last_error()
     assert lib.pgtt_adam_scratch_floats() > 0
+    # round-2 learner entry points: the same contract (argument errors before any CUDA call)
+    assert lib.pgtt_step_launches(null) == -1
+    assert lib.pgtt_gae_moments(null, null, null, null, 0, 0, 0.95, 0.97, 1.0, null, null, null, null) == -1 and b"pgtt_gae_moments" in lib.pgtt_policy_last_error()
+    assert lib.pgtt_gae_sums(null, null, null, null, 20, 2048, 0.95, 0.97, 1.0, null, null, null, null) == -1
+    assert lib.pgtt_moments_finalize(null, null, null) == -1
+    assert lib.pgtt_minibatch_gather(null, null, 0, 0, 0, 0, 0, null, null, null, null, null, null, null, null) == -1
+    assert lib.pgtt_col_moments(null, 0, 0, 0, null, null, null) == -1 and lib.pgtt_col_moments_scratch_doubles(171) == 592 * 2 * 171
+    assert lib.pgtt_policy_set_params_device(null, None, None, null, null, null) == -1
+    lib.pgtt_mlp_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p(0)
+    assert lib.pgtt_mlp_create(0, (ctypes.c_int * 1)(4), 8, 0, ctypes.byref(h)) == -1 and b"pgtt_mlp_create" in lib.pgtt_mlp_last_error()
+    assert lib.pgtt_mlp_create(2, (ctypes.c_int * 3)(4, 5000, 2), 8, 0, ctypes.byref(h)) == -1            # width out of range
+    assert h.value is None
+    assert lib.pgtt_mlp_forward(null, null, 0, None, None, null, null) == -1 and lib.pgtt_mlp_backward(null, null, None, None, null) == -1
+    assert lib.pgtt_mlp_forward_gather(null, null, 0, 0, null, 0, null, null, None, None, null, null) == -1
+    assert lib.pgtt_mlp_rows(null) == 0
+    lib.pgtt_mlp_destroy(null)                                                                          # destroying nothing is fine
